@@ -1,0 +1,109 @@
+/* libmmx — C ABI of the B200 (sm_100a) ConvMixer / MotionMixer hot path.
+ *
+ * The reference (AlekseiZhuravlev/MotionMixerConv) is pure Python/PyTorch and has no FFI of its
+ * own: its "plugin interface" for this path is the nn.Module surface
+ *     h36m/mlp_mixer.py:254-258,306        MlpMixer(...).forward(x)
+ *     h36m/conv_mixer_model.py:357-379,428 ConvMixer(...).forward(x)
+ *     h36m/utils/utils_mixer.py:48         mpjpe_error(pred, gt)
+ *     h36m/train_mixer_h36m.py:63,193      optim.Adam(...).step()
+ * The Python package motionmixerconv_b200 mirrors that surface and binds the entry points below
+ * with ctypes (INTEGRATION.md shows the stub).  Each entry point cites the reference code whose
+ * arithmetic it replaces.
+ *
+ * Conventions: all tensors fp32, contiguous, row-major, DEVICE pointers borrowed from the caller
+ * (torch's caching allocator).  Nothing here allocates, frees or synchronises; kernels are
+ * enqueued on `stream` (a cudaStream_t) of the CURRENT device.  Gradient outputs are
+ * ACCUMULATED (+=, RED.ADD) so the caller zeroes them once per step.  Return value: 0 on
+ * success, negative on error (MMX_E_*); mmx_last_error() gives a thread-local message.
+ */
+#ifndef MMX_H_
+#define MMX_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMX_OK 0
+#define MMX_E_INVALID (-1)     /* bad argument (null pointer, non-positive size, ...) */
+#define MMX_E_UNSUPPORTED (-2) /* shape outside what the kernels are built for */
+#define MMX_E_CUDA (-3)        /* CUDA runtime error (message has the cudaError string) */
+
+#define MMX_ACT_GELU 0
+#define MMX_ACT_MISH 1
+
+int mmx_version(void);
+const char* mmx_last_error(void);
+
+/* Dropout (nn.Dropout sites inside the blocks; mlp_mixer.py:68-70, conv_mixer_model.py:113-114).
+ * Masks are Philox4x32-10(key = seed, counter = (element/4, 0.., site, step)); p == 0 disables. */
+typedef struct {
+    float p;
+    unsigned long long seed;
+    unsigned int step;
+} MmxDropout;
+
+/* ---------------- MlpMixer (h36m/mlp_mixer.py) ---------------- */
+
+/* One MixerBlock (mlp_mixer.py:100-164).  Parameter pointers use the reference layouts. */
+typedef struct {
+    float *ln1_w, *ln1_b;   /* LN1.weight, LN1.bias                               [H]          */
+    float *tok_w1, *tok_b1; /* mlp_block_token_mixing.fc1.{weight,bias}           [tok,T],[tok]*/
+    float *tok_w2, *tok_b2; /* mlp_block_token_mixing.fc2.{weight,bias}           [T,tok],[T]  */
+    float *ln2_w, *ln2_b;   /* LN2.weight, LN2.bias                               [H]          */
+    float *ch_w1, *ch_b1;   /* mlp_block_channel_mixing.fc1.{weight,bias}         [ch,H],[ch]  */
+    float *ch_w2, *ch_b2;   /* mlp_block_channel_mixing.fc2.{weight,bias}         [H,ch],[H]   */
+    float *se_w1, *se_w2;   /* se.excitation.0.weight [T/r,T], se.excitation.2.weight [T,T/r]; null if !use_se */
+} MmxMlpBlockParams;
+
+typedef struct {
+    int B, T, H, tok, ch; /* batch, seq_len, hidden_dim, tokens_mlp_dim, channels_mlp_dim */
+    int se_hidden;        /* T / r_se */
+    int act;              /* MMX_ACT_* */
+    int use_se, use_max_pooling;
+    int training;         /* dropout active only when training != 0 */
+    int block_index;      /* selects the dropout sites of this block */
+    MmxDropout dropout;
+} MmxMlpBlockDesc;
+
+/* y = MixerBlock(x): LN1 -> token MLP -> SE -> +res -> LN2 -> channel MLP -> SE -> +res, fused.
+ * Replaces MixerBlock.forward, mlp_mixer.py:138-164. x,y: [B,T,H]. */
+int mmx_mlp_block_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* y, void* stream);
+/* Backward of the same (autograd of mlp_mixer.py:138-164); the forward is recomputed from x.
+ * dx: [B,T,H] written; grads: accumulated. */
+int mmx_mlp_block_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads,
+                      const float* x, const float* dy, float* dx, void* stream);
+
+/* y[r,:] = W x[r,:] + b  — MlpMixer.conv (Conv2d(1,H,(1,D)) == per-frame Linear, mlp_mixer.py:268,325-327)
+ * and PoseEncoder.embed_mlp without harmonics (positional_encoder.py:91).  x:[rows,K] w:[N,K] y:[rows,N]. */
+int mmx_linear_fwd(int rows, int K, int N, const float* x, const float* w, const float* b, float* y, void* stream);
+/* dw,db accumulated; dx (may be null) written. */
+int mmx_linear_bwd(int rows, int K, int N, const float* x, const float* w, const float* dy, float* dw, float* db,
+                   float* dx, void* stream);
+
+typedef struct {
+    float *ln_w, *ln_b;  /* LN.weight, LN.bias            [H]            */
+    float *wt, *bt;      /* conv_out.weight [To,T,1], conv_out.bias [To] */
+    float *wf, *bf;      /* fc_out.weight [D,H], fc_out.bias [D]         */
+} MmxMlpHeadParams;
+typedef struct { int B, T, To, H, D; } MmxMlpHeadDesc;
+
+/* out = fc_out(conv_out(LN(x)))  — mlp_mixer.py:332-335.  x:[B,T,H] out:[B,To,D]. */
+int mmx_mlp_head_fwd(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const float* x, float* out, void* stream);
+int mmx_mlp_head_bwd(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const MmxMlpHeadParams* grads,
+                     const float* x, const float* dout, float* dx, void* stream);
+
+/* ---------------- loss / optimiser ---------------- */
+
+/* MPJPE (utils_mixer.py:48-53): *loss_sum += sum_joints ||gt - pred||_2 (caller zeroes it; mean =
+ * loss_sum / n_joints); dpred (nullable) = gscale * dL/dpred of the MEAN, 0 at zero distance. */
+int mmx_mpjpe_fwd_bwd(const float* pred, const float* gt, float* dpred, float* loss_sum, long long n_joints,
+                      float gscale, void* stream);
+
+/* torch.optim.Adam (coupled L2) on flat buffers — train_mixer_h36m.py:63,193.
+ * hyper (DEVICE, 8 floats): lr, beta1, beta2, eps, weight_decay, 1-beta1^t, sqrt(1-beta2^t), grad_scale. */
+int mmx_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* hyper, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMX_H_ */

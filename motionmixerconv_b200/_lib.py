@@ -1,0 +1,127 @@
+"""ctypes binding of libmmx.so (the C ABI declared in include/mmx.h).
+
+There is exactly one implementation behind these entry points: the sm_100a CUDA kernels in
+``csrc/``.  If the shared library is missing or cannot be loaded this module raises — there is
+no CPU or PyTorch fallback anywhere in the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmx.so")
+
+MMX_ACT = {"gelu": 0, "mish": 1}
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class MmxDropout(C.Structure):
+    _fields_ = [("p", C.c_float), ("seed", C.c_ulonglong), ("step", C.c_uint)]
+
+
+class MmxMlpBlockParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ln1_w", "ln1_b", "tok_w1", "tok_b1", "tok_w2", "tok_b2", "ln2_w", "ln2_b",
+        "ch_w1", "ch_b1", "ch_w2", "ch_b2", "se_w1", "se_w2")]
+
+
+class MmxMlpBlockDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("T", C.c_int), ("H", C.c_int), ("tok", C.c_int), ("ch", C.c_int),
+                ("se_hidden", C.c_int), ("act", C.c_int), ("use_se", C.c_int), ("use_max_pooling", C.c_int),
+                ("training", C.c_int), ("block_index", C.c_int), ("dropout", MmxDropout)]
+
+
+class MmxMlpHeadParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln_w", "ln_b", "wt", "bt", "wf", "bf")]
+
+
+class MmxMlpHeadDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("T", C.c_int), ("To", C.c_int), ("H", C.c_int), ("D", C.c_int)]
+
+
+class MmxConvBlockParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ln1_w", "ln1_b", "conv1_w", "conv1_b", "ln2_w", "ln2_b", "conv2_w", "conv2_b", "se_w1", "se_w2")]
+
+
+class MmxConvBlockDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("C", C.c_int), ("T", C.c_int), ("E", C.c_int),
+                ("k1t", C.c_int), ("k1p", C.c_int), ("p1t", C.c_int), ("p1p", C.c_int),
+                ("k2t", C.c_int), ("k2p", C.c_int), ("p2t", C.c_int), ("p2p", C.c_int),
+                ("twice", C.c_int), ("se_hidden", C.c_int), ("act", C.c_int), ("use_se", C.c_int),
+                ("use_max_pooling", C.c_int), ("training", C.c_int), ("block_index", C.c_int),
+                ("dropout", MmxDropout)]
+
+
+class MmxConvHeadParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln_w", "ln_b", "wt", "bt", "wp", "bp", "wf", "bf")]
+
+
+class MmxConvHeadDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("C", C.c_int), ("T", C.c_int), ("To", C.c_int), ("E", C.c_int), ("D", C.c_int)]
+
+
+class MmxEncoderDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("T", C.c_int), ("D", C.c_int), ("E", C.c_int), ("C", C.c_int), ("n_harmonic", C.c_int)]
+
+
+class MmxEncoderParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("freq", "w", "b", "wc", "bc")]
+
+
+# name -> (restype, argtypes).  Everything declared in include/mmx.h must appear here
+# (tests/test_abi.py checks the two lists against each other and against the built library).
+SIGNATURES = {
+    "mmx_version": (C.c_int, []),
+    "mmx_last_error": (C.c_char_p, []),
+    "mmx_mlp_block_fwd": (C.c_int, [C.POINTER(MmxMlpBlockDesc), C.POINTER(MmxMlpBlockParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_mlp_block_bwd": (C.c_int, [C.POINTER(MmxMlpBlockDesc), C.POINTER(MmxMlpBlockParams), C.POINTER(MmxMlpBlockParams),
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_linear_fwd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_linear_bwd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    "mmx_mlp_head_fwd": (C.c_int, [C.POINTER(MmxMlpHeadDesc), C.POINTER(MmxMlpHeadParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_mlp_head_bwd": (C.c_int, [C.POINTER(MmxMlpHeadDesc), C.POINTER(MmxMlpHeadParams), C.POINTER(MmxMlpHeadParams),
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_mpjpe_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p]),
+    "mmx_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+}
+
+
+class MmxError(RuntimeError):
+    pass
+
+
+def bind(cdll):
+    """Attach restype/argtypes for every entry point; raises AttributeError on a missing symbol."""
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(cdll, name)
+        fn.restype = res
+        fn.argtypes = args
+    return cdll
+
+
+_lib = None
+
+
+def load():
+    """Load libmmx.so (built by ``python -m motionmixerconv_b200.build`` / ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MmxError(
+                "motionmixerconv_b200: %s not found — the CUDA extension is not built. Run "
+                "`python -m motionmixerconv_b200.build` (needs nvcc). There is no CPU fallback." % LIB_PATH)
+        _lib = bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def check(lib, rc, what):
+    if rc != 0:
+        msg = lib.mmx_last_error()
+        text = msg.decode() if msg else "?"
+        if rc == -1:
+            raise ValueError("%s: %s" % (what, text))
+        raise MmxError("%s failed (%d): %s" % (what, rc, text))

@@ -1,0 +1,24 @@
+// mmx_mlp_block_bwd: fused MixerBlock backward (include/mmx.h).
+#define MMX_BWD_ACT mmx::ACT_GELU
+#define MMX_BWD_NAME mmx_mlp_bwd_launch_gelu
+#define MMX_BWD_NS mmx_tu_bwd_gelu
+#include "mmx_api_mlp_bwd.inl"
+
+int mmx_mlp_bwd_launch_mish(const mmx::MlpBlockBwdArgs& a, int wt1, int grid, size_t smem, void* stream);
+
+extern "C" int mmx_mlp_block_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads,
+                                 const float* x, const float* dy, float* dx, void* stream) {
+    if (!x || !dy || !dx) return fail(MMX_E_INVALID, "mmx_mlp_block_bwd: null tensor");
+    MlpBlockBwdArgs a;
+    size_t smem; int grid;
+    int rc = plan_mlp_block(d, true, &a.d, &smem, &grid);
+    if (rc) return rc;
+    if ((rc = check_block_params(w, d->use_se, "mmx_mlp_block_bwd"))) return rc;
+    if ((rc = check_block_params(grads, d->use_se, "mmx_mlp_block_bwd(grads)"))) return rc;
+    a.dr = make_dropout(d->dropout, d->training);
+    a.w = to_w(w); a.g = to_w(grads); a.x = x; a.dy = dy; a.dx = dx;
+    const int tiles = imax(((d->ch + 3) / 4) * ((d->H + 3) / 4), 1);
+    const int wt1 = tiles <= kThreads;
+    return d->act == MMX_ACT_GELU ? mmx_mlp_bwd_launch_gelu(a, wt1, grid, smem, stream)
+                                  : mmx_mlp_bwd_launch_mish(a, wt1, grid, smem, stream);
+}

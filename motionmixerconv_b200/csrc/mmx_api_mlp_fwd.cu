@@ -1,0 +1,28 @@
+// mmx_mlp_block_fwd: fused MixerBlock forward (include/mmx.h).
+#include "mmx_mlp_host.cuh"
+
+using namespace mmx;
+
+namespace mmx_tu_mlp_fwd {
+template <int ACT, int TC, int TOKC>
+struct MlpFwdBody { static MMX_D void run(Exec& ex, const MlpBlockFwdArgs& a) { mlp_block_fwd_body<ACT, TC, TOKC>(ex, a); } };
+
+template <int ACT>
+int dispatch_mlp_fwd(const MlpBlockFwdArgs& a, int grid, size_t smem, void* stream) {
+    if (a.d.T == 10 && a.d.tok == 20) return launch<MlpFwdBody<ACT, 10, 20>>(a, grid, kThreads, smem, stream, 1);
+    return launch<MlpFwdBody<ACT, 0, 0>>(a, grid, kThreads, smem, stream, 1);
+}
+}  // namespace mmx_tu_mlp_fwd
+using namespace mmx_tu_mlp_fwd;
+
+extern "C" int mmx_mlp_block_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* y, void* stream) {
+    if (!x || !y) return fail(MMX_E_INVALID, "mmx_mlp_block_fwd: null tensor");
+    MlpBlockFwdArgs a;
+    size_t smem; int grid;
+    int rc = plan_mlp_block(d, false, &a.d, &smem, &grid);
+    if (rc) return rc;
+    if ((rc = check_block_params(w, d->use_se, "mmx_mlp_block_fwd"))) return rc;
+    a.dr = make_dropout(d->dropout, d->training);
+    a.w = to_w(w); a.x = x; a.y = y;
+    return d->act == MMX_ACT_GELU ? dispatch_mlp_fwd<ACT_GELU>(a, grid, smem, stream) : dispatch_mlp_fwd<ACT_MISH>(a, grid, smem, stream);
+}

@@ -1,0 +1,210 @@
+"""torch.autograd.Function wrappers over the libmmx C ABI (include/mmx.h).
+
+Every op here launches hand-written sm_100a kernels on ``torch.cuda.current_stream()``; inputs must
+be CUDA fp32 tensors.  There is no CPU / eager-PyTorch implementation: non-CUDA input raises.
+Backward runs on PyTorch's autograd worker thread — the C ABI holds no thread-local CUDA state and
+takes the stream explicitly, and we re-enter the tensor's device before every call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("motionmixerconv_b200: %s must be a CUDA tensor (the hot path has no CPU implementation)" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("motionmixerconv_b200: %s must be float32, got %s" % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _zeros_like_many(tensors):
+    """One memset for all gradient buffers: a flat zero buffer sliced into views (16-byte aligned)."""
+    sizes = [0 if t is None else (t.numel() + 3) // 4 * 4 for t in tensors]
+    ref = next(t for t in tensors if t is not None)
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=ref.device)
+    out, o = [], 0
+    for t, n in zip(tensors, sizes):
+        out.append(None if t is None else flat[o:o + t.numel()].view(t.shape))
+        o += n
+    return out
+
+
+def _call(name, *args):
+    lib = L.load()
+    L.check(lib, getattr(lib, name)(*args), name)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-frame linear layer (MlpMixer.conv, mlp_mixer.py:325-327)
+# ------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w, b = _chk(x, "x"), _chk(w, "weight"), _chk(b, "bias")
+        K, N = x.shape[-1], b.numel()
+        rows = x.numel() // K
+        y = torch.empty(*x.shape[:-1], N, dtype=torch.float32, device=x.device)
+        with torch.cuda.device_of(x):
+            _call("mmx_linear_fwd", rows, K, N, _p(x), _p(w), _p(b), _p(y), _stream())
+        ctx.save_for_backward(x, w)
+        ctx.need_dx = x.requires_grad
+        ctx.wshape = w.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _chk(dy, "grad")
+        K, N = x.shape[-1], dy.shape[-1]
+        rows = x.numel() // K
+        dw, db = _zeros_like_many([w, dy.new_empty(N)])
+        dx = torch.empty_like(x) if ctx.need_dx else None
+        with torch.cuda.device_of(x):
+            _call("mmx_linear_bwd", rows, K, N, _p(x), _p(w), _p(dy), _p(dw), _p(db), _p(dx), _stream())
+        return dx, dw.view(ctx.wshape), db
+
+
+def linear(x, weight, bias):
+    return _Linear.apply(x, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------------
+# MixerBlock (mlp_mixer.py:138-164)
+# ------------------------------------------------------------------------------------------------
+_BLOCK_FIELDS = ("ln1_w", "ln1_b", "tok_w1", "tok_b1", "tok_w2", "tok_b2", "ln2_w", "ln2_b",
+                 "ch_w1", "ch_b1", "ch_w2", "ch_b2", "se_w1", "se_w2")
+
+
+def mlp_block_table(tensors):
+    t = L.MmxMlpBlockParams()
+    for f, v in zip(_BLOCK_FIELDS, tensors):
+        setattr(t, f, _p(v))
+    return t
+
+
+def mlp_block_desc(B, T, H, tok, ch, se_hidden, act, use_se, use_max, training, block_index, p, seed, step):
+    return L.MmxMlpBlockDesc(B, T, H, tok, ch, se_hidden, L.MMX_ACT[act], int(use_se), int(use_max), int(training),
+                             block_index, L.MmxDropout(float(p), int(seed), int(step)))
+
+
+class _MlpBlock(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, meta, *params):
+        x = _chk(x, "x")
+        params = [None if q is None else _chk(q, "parameter") for q in params]
+        B, T, H = x.shape
+        desc = mlp_block_desc(B, T, H, *meta)
+        y = torch.empty_like(x)
+        with torch.cuda.device_of(x):
+            _call("mmx_mlp_block_fwd", C.byref(desc), C.byref(mlp_block_table(params)), _p(x), _p(y), _stream())
+        ctx.save_for_backward(x, *[q for q in params if q is not None])
+        ctx.has = [q is not None for q in params]
+        ctx.meta = meta
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, *rest = ctx.saved_tensors
+        it = iter(rest)
+        params = [next(it) if h else None for h in ctx.has]
+        dy = _chk(dy, "grad")
+        B, T, H = x.shape
+        desc = mlp_block_desc(B, T, H, *ctx.meta)
+        grads = _zeros_like_many(params)
+        dx = torch.empty_like(x)
+        with torch.cuda.device_of(x):
+            _call("mmx_mlp_block_bwd", C.byref(desc), C.byref(mlp_block_table(params)), C.byref(mlp_block_table(grads)),
+                  _p(x), _p(dy), _p(dx), _stream())
+        return (dx, None, *grads)
+
+
+def mlp_block(x, meta, params):
+    """meta = (tok, ch, se_hidden, act, use_se, use_max, training, block_index, p, seed, step)."""
+    return _MlpBlock.apply(x, meta, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+# MlpMixer head (mlp_mixer.py:332-335)
+# ------------------------------------------------------------------------------------------------
+_HEAD_FIELDS = ("ln_w", "ln_b", "wt", "bt", "wf", "bf")
+
+
+def mlp_head_table(tensors):
+    t = L.MmxMlpHeadParams()
+    for f, v in zip(_HEAD_FIELDS, tensors):
+        setattr(t, f, _p(v))
+    return t
+
+
+class _MlpHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, wt, bt, wf, bf):
+        x = _chk(x, "x")
+        params = [_chk(q, "parameter") for q in (ln_w, ln_b, wt, bt, wf, bf)]
+        B, T, H = x.shape
+        To, D = bt.numel(), bf.numel()
+        desc = L.MmxMlpHeadDesc(B, T, To, H, D)
+        out = torch.empty(B, To, D, dtype=torch.float32, device=x.device)
+        with torch.cuda.device_of(x):
+            _call("mmx_mlp_head_fwd", C.byref(desc), C.byref(mlp_head_table(params)), _p(x), _p(out), _stream())
+        ctx.save_for_backward(x, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, *params = ctx.saved_tensors
+        dout = _chk(dout, "grad")
+        B, T, H = x.shape
+        To, D = params[3].numel(), params[5].numel()
+        desc = L.MmxMlpHeadDesc(B, T, To, H, D)
+        grads = _zeros_like_many(params)
+        dx = torch.empty_like(x)
+        with torch.cuda.device_of(x):
+            _call("mmx_mlp_head_bwd", C.byref(desc), C.byref(mlp_head_table(params)), C.byref(mlp_head_table(grads)),
+                  _p(x), _p(dout), _p(dx), _stream())
+        return (dx, *grads)
+
+
+def mlp_head(x, ln_w, ln_b, wt, bt, wf, bf):
+    return _MlpHead.apply(x, ln_w, ln_b, wt, bt, wf, bf)
+
+
+# ------------------------------------------------------------------------------------------------
+# MPJPE (utils_mixer.py:48-53)
+# ------------------------------------------------------------------------------------------------
+class _Mpjpe(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, gt):
+        pred, gt = _chk(pred, "batch_pred"), _chk(gt, "batch_gt")
+        if pred.numel() != gt.numel() or pred.numel() % 3:
+            raise RuntimeError("mpjpe_error: shapes %s / %s are not matching [*, 3] joint arrays" % (tuple(pred.shape), tuple(gt.shape)))
+        n = pred.numel() // 3
+        loss_sum = torch.zeros(1, dtype=torch.float32, device=pred.device)
+        dpred = torch.empty_like(pred) if pred.requires_grad else None
+        with torch.cuda.device_of(pred):
+            _call("mmx_mpjpe_fwd_bwd", _p(pred), _p(gt), _p(dpred), _p(loss_sum), n, 1.0, _stream())
+        ctx.save_for_backward(dpred)
+        return (loss_sum / n).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dpred,) = ctx.saved_tensors
+        return dpred * g, None
+
+
+def mpjpe_error(batch_pred, batch_gt):
+    """Drop-in for ``h36m.utils.utils_mixer.mpjpe_error`` (one fused kernel: loss + dL/dpred)."""
+    return _Mpjpe.apply(batch_pred, batch_gt)
