@@ -35,11 +35,13 @@ int mmx_version(void);
 const char* mmx_last_error(void);
 
 /* Dropout (nn.Dropout sites inside the blocks; mlp_mixer.py:68-70, conv_mixer_model.py:113-114).
- * Masks are Philox4x32-10(key = seed, counter = (element/4, 0.., site, step)); p == 0 disables. */
+ * Masks are Philox4x32-10(key = seed, counter = (element/4, 0.., site, step + *step_dev)); p == 0 disables. */
 typedef struct {
     float p;
     unsigned long long seed;
-    unsigned int step;
+    unsigned int step;            /* host-side step counter ...                                   */
+    const unsigned int* step_dev; /* ... plus (if non-null) a DEVICE counter read by the kernel, so a
+                                     launch recorded in a CUDA graph draws fresh masks on every replay */
 } MmxDropout;
 
 /* ---------------- MlpMixer (h36m/mlp_mixer.py) ---------------- */
@@ -102,6 +104,9 @@ int mmx_mpjpe_fwd_bwd(const float* pred, const float* gt, float* dpred, float* l
 /* torch.optim.Adam (coupled L2) on flat buffers — train_mixer_h36m.py:63,193.
  * hyper (DEVICE, 8 floats): lr, beta1, beta2, eps, weight_decay, 1-beta1^t, sqrt(1-beta2^t), grad_scale. */
 int mmx_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* hyper, void* stream);
+/* Device-side optimiser clock: ++*step (DEVICE uint32, also the dropout step_dev); hyper[5], hyper[6] are
+ * recomputed from hyper[1], hyper[2] and the new step.  Lets a CUDA graph replay a whole training step. */
+int mmx_adam_advance(float* hyper, unsigned int* step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ c_float_p = C.POINTER(C.c_float)
 
 
 class MmxDropout(C.Structure):
-    _fields_ = [("p", C.c_float), ("seed", C.c_ulonglong), ("step", C.c_uint)]
+    _fields_ = [("p", C.c_float), ("seed", C.c_ulonglong), ("step", C.c_uint), ("step_dev", C.c_void_p)]
 
 
 class MmxMlpBlockParams(C.Structure):
@@ -87,6 +87,7 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_mpjpe_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p]),
     "mmx_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "mmx_adam_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import concurrent.futures as cf
 import os
+import re
 import subprocess
 import sys
 
@@ -24,15 +25,25 @@ def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _deps():
-    out = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    out.append(os.path.join(os.path.dirname(HERE), "include", "mmx.h"))
-    return out
+_INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+
+
+def _deps(src, seen=None):
+    """Transitive quoted includes of one translation unit (so editing a header only rebuilds its users)."""
+    seen = set() if seen is None else seen
+    src = os.path.normpath(src)
+    if src in seen or not os.path.exists(src):
+        return seen
+    seen.add(src)
+    with open(src) as f:
+        for inc in _INC.findall(f.read()):
+            _deps(os.path.join(os.path.dirname(src), inc), seen)
+    return seen
 
 
 def _compile(src, verbose):
     obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-    newest = max(os.path.getmtime(d) for d in _deps())
+    newest = max(os.path.getmtime(d) for d in _deps(src))
     if os.path.exists(obj) and os.path.getmtime(obj) >= newest:
         return obj, ""
     cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]

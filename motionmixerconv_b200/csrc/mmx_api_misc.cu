@@ -31,6 +31,7 @@ template <int TC, int WT>
 struct HeadBwdBody { static MMX_D void run(Exec& ex, const MlpHeadBwdArgs& a) { mlp_head_bwd_body<TC, WT>(ex, a); } };
 struct MpjpeBody { static MMX_D void run(Exec& ex, const MpjpeArgs& a) { mpjpe_body(ex, a); } };
 struct AdamBody { static MMX_D void run(Exec& ex, const AdamArgs& a) { adam_body(ex, a); } };
+struct AdamAdvanceBody { static MMX_D void run(Exec& ex, const AdamAdvanceArgs& a) { adam_advance_body(ex, a); } };
 
 int plan_linear(int rows, int K, int N, bool bwd, LinearDims* out, size_t* smem, int* grid) {
     if (rows <= 0 || K <= 0 || N <= 0) return fail(MMX_E_INVALID, "non-positive dimension");
@@ -169,6 +170,12 @@ int mmx_adam_step(float* p, const float* g, float* m, float* v, long long n, con
     const long long want = ((n >> 2) + kThreads - 1) / kThreads + 1;
     const int grid = (int)(want < (long long)di.sms * 8 ? want : (long long)di.sms * 8);
     return launch<AdamBody>(a, grid, kThreads, 16, stream, 1);
+}
+
+int mmx_adam_advance(float* hyper, unsigned int* step, void* stream) {
+    if (!hyper || !step) return fail(MMX_E_INVALID, "mmx_adam_advance: null pointer");
+    AdamAdvanceArgs a; a.hp = hyper; a.step = step;
+    return launch<AdamAdvanceBody>(a, 1, 32, 16, stream, 1);
 }
 
 }  // extern "C"

@@ -51,6 +51,15 @@ MMX_D void red_add(float* p, float v) {
 #if defined(MMX_HOST_EMU)
     *p += v;
 #else
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+#endif
+}
+
+// shared-memory accumulate from several threads of the CTA (ATOMS on the GPU)
+MMX_D void smem_add(float* p, float v) {
+#if defined(MMX_HOST_EMU)
+    *p += v;
+#else
     atomicAdd(p, v);
 #endif
 }
@@ -139,7 +148,13 @@ struct Dropout {
     uint32_t step;               // training step counter (c3)
     uint32_t thresh;             // keep iff r >= thresh, thresh = round(p * 2^32) (0 => no dropout)
     float scale;                 // 1/(1-p)
+    const uint32_t* step_ptr;    // optional device-resident addend to `step` (CUDA-graph replays)
 };
+
+MMX_D Dropout resolve_dropout(Dropout d) {
+    if (d.step_ptr) d.step += *d.step_ptr;
+    return d;
+}
 
 // keep-scale (0 or 1/(1-p)) for element `elem` of dropout site `site`
 #if defined(MMX_HOST_EMU)

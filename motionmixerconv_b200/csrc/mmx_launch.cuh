@@ -96,6 +96,7 @@ static inline Dropout make_dropout(const MmxDropout& s, int training) {
     d.seed_lo = (uint32_t)(s.seed & 0xffffffffull);
     d.seed_hi = (uint32_t)(s.seed >> 32);
     d.step = s.step;
+    d.step_ptr = s.step_dev;
     if (training && s.p > 0.0f) {
         double t = (double)s.p * 4294967296.0;
         d.thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)(t + 0.5);

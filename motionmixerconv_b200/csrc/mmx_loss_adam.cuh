@@ -88,4 +88,21 @@ MMX_D void adam_body(Exec& ex, const AdamArgs& a) {
     });
 }
 
+// Advance the device-resident optimiser clock (one thread): t = ++*step; refresh the bias
+// corrections hp[5] = 1-beta1^t, hp[6] = sqrt(1-beta2^t).  Lets lr-independent per-step state
+// live on the device so the whole step can be replayed from a CUDA graph without host writes.
+struct AdamAdvanceArgs { float* hp; unsigned int* step; };
+
+MMX_D void adam_advance_body(Exec& ex, const AdamAdvanceArgs& a) {
+    ex.phase([&](int tid) {
+        if (ex.bid == 0 && tid == 0) {
+            const unsigned int t = *a.step + 1u;
+            *a.step = t;
+            const double b1 = (double)a.hp[1], b2 = (double)a.hp[2];
+            a.hp[5] = (float)(1.0 - pow(b1, (double)t));
+            a.hp[6] = (float)sqrt(1.0 - pow(b2, (double)t));
+        }
+    });
+}
+
 }  // namespace mmx

@@ -45,7 +45,7 @@ struct MlpBlockSmem {
     int mean1, rstd1, mean2, rstd2, pool1, gate1, pool2, gate2, z1, z2, amax1, amax2;
     int dq, dz, ds1, ds2;
     // gradient accumulators owned by single threads (backward only)
-    int a_ln1g, a_ln1b, a_ln2g, a_ln2b, a_cb1, a_cb2, a_se1, a_se2;
+    int a_ln1g, a_ln1b, a_ln2g, a_ln2b, a_cb1, a_cb2, a_se1, a_se2, a_tb1, a_tb2;
     // activation tiles
     int bX, bD, bYt, scratch;
     int bX1, bA, bY2, bU, bG;          // channel-half view of scratch
@@ -73,8 +73,9 @@ MMX_HD MlpBlockSmem mlp_block_smem(const MlpDims& d, bool bwd) {
     if (bwd) {
         L.a_ln1g = take(H); L.a_ln1b = take(H); L.a_ln2g = take(H); L.a_ln2b = take(H);
         L.a_cb1 = take(ch); L.a_cb2 = take(H); L.a_se1 = take(rr * T); L.a_se2 = take(T * rr);
+        L.a_tb1 = take(tok); L.a_tb2 = take(T);
     } else {
-        L.a_ln1g = L.a_ln1b = L.a_ln2g = L.a_ln2b = L.a_cb1 = L.a_cb2 = L.a_se1 = L.a_se2 = -1;
+        L.a_ln1g = L.a_ln1b = L.a_ln2g = L.a_ln2b = L.a_cb1 = L.a_cb2 = L.a_se1 = L.a_se2 = L.a_tb1 = L.a_tb2 = -1;
     }
     const int RH = L.R * L.PH, RC = L.R * L.PC;
     L.bX = take(RH);
@@ -257,7 +258,8 @@ MMX_D void mlp_block_fwd_body(Exec& ex, const MlpBlockFwdArgs& a) {
     const float* V1 = d.w_in_smem ? sm + L.cw1 : a.w.cw1;
     const float* V2 = d.w_in_smem ? sm + L.cw2 : a.w.cw2;
     const int ldv1 = d.w_in_smem ? PH : H, ldv2 = d.w_in_smem ? PC : ch;
-    const bool drop = d.training && a.dr.thresh != 0u;
+    const Dropout dr = resolve_dropout(a.dr);
+    const bool drop = d.training && dr.thresh != 0u;
 
     ex.phase([&](int tid) { mlp_stage_weights(tid, nthr, sm, L, d, a.w); });
 
@@ -282,7 +284,7 @@ MMX_D void mlp_block_fwd_body(Exec& ex, const MlpBlockFwdArgs& a) {
             TokenMix<ACT, TC, TOKC> tm;
             for (int p = tid; p < ns * H; p += nthr) {
                 const int s = p / H, h = p - s * H;
-                tm.fwd(sm, L, d, a.dr, s, h, seq0);
+                tm.fwd(sm, L, d, dr, s, h, seq0);
                 MMX_UNROLL
                 for (int t = 0; t < (TC > 0 ? TC : T); ++t)
                     sm[L.bA + (s * T + t) * PH + h] = tm.y[t];
@@ -319,14 +321,14 @@ MMX_D void mlp_block_fwd_body(Exec& ex, const MlpBlockFwdArgs& a) {
         ex.phase([&](int tid) {
             gemm_nt<4, 4>(tid, nthr, sm + L.bA, PH, V1, ldv1, nr, ch, H, [&](int m, int n, float v) {
                 float gv = act_fwd<ACT>(v + sm[L.cb1 + n]);
-                if (drop) gv *= dropout_scale(a.dr, d.site_base + 2, ((unsigned long long)seq0 * T + m) * ch + n);
+                if (drop) gv *= dropout_scale(dr, d.site_base + 2, ((unsigned long long)seq0 * T + m) * ch + n);
                 sm[L.bG + m * PC + n] = gv;
             });
         });
         ex.phase([&](int tid) {
             gemm_nt<4, 4>(tid, nthr, sm + L.bG, PC, V2, ldv2, nr, H, ch, [&](int m, int n, float v) {
                 float yv = v + sm[L.cb2 + n];
-                if (drop) yv *= dropout_scale(a.dr, d.site_base + 3, ((unsigned long long)seq0 * T + m) * H + n);
+                if (drop) yv *= dropout_scale(dr, d.site_base + 3, ((unsigned long long)seq0 * T + m) * H + n);
                 sm[L.bA + m * PH + n] = yv;
             });
         });
@@ -381,7 +383,6 @@ struct MlpBwdRegs {
     float dV2[WT][4][4];   // dL/d cw2 tiles  [H][ch]
     float dW1[4][4];       // dL/d tw1 tile   [tok][T]   (split-K slice)
     float dW2[4][4];       // dL/d tw2 tile   [T][tok]
-    float db1[64], db2[32];
 };
 
 // SE backward for one squeeze-excitation use.  Inputs (shared): dg[r] = sum_h dOut*Y (in L.dq),
@@ -435,7 +436,8 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
     const float* V1 = d.w_in_smem ? sm + L.cw1 : a.w.cw1;
     const float* V2 = d.w_in_smem ? sm + L.cw2 : a.w.cw2;
     const int ldv1 = d.w_in_smem ? PH : H, ldv2 = d.w_in_smem ? PC : ch;
-    const bool drop = d.training && a.dr.thresh != 0u;
+    const Dropout dr = resolve_dropout(a.dr);
+    const bool drop = d.training && dr.thresh != 0u;
     const float invH = 1.0f / (float)H;
 
     // weight-gradient tiling
@@ -456,6 +458,7 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
         zero_vec(tid, nthr, sm + L.a_ln2g, H); zero_vec(tid, nthr, sm + L.a_ln2b, H);
         zero_vec(tid, nthr, sm + L.a_cb1, ch); zero_vec(tid, nthr, sm + L.a_cb2, H);
         zero_vec(tid, nthr, sm + L.a_se1, rr * T); zero_vec(tid, nthr, sm + L.a_se2, T * rr);
+        zero_vec(tid, nthr, sm + L.a_tb1, tok); zero_vec(tid, nthr, sm + L.a_tb2, T);
         MlpBwdRegs<WT>& rg = regs[tid];
         MMX_UNROLL
         for (int w = 0; w < WT; ++w)
@@ -467,10 +470,6 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
         for (int i = 0; i < 4; ++i)
             MMX_UNROLL
             for (int j = 0; j < 4; ++j) { rg.dW1[i][j] = 0.0f; rg.dW2[i][j] = 0.0f; }
-        MMX_UNROLL
-        for (int k = 0; k < (TOKC > 0 ? TOKC : tok); ++k) rg.db1[k] = 0.0f;
-        MMX_UNROLL
-        for (int t = 0; t < (TC > 0 ? TC : T); ++t) rg.db2[t] = 0.0f;
     });
 
     const int ntiles = (d.B + S - 1) / S;
@@ -505,7 +504,7 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
             TokenMix<ACT, TC, TOKC> tm;
             for (int p = tid; p < ns * H; p += nthr) {
                 const int s = p / H, h = p - s * H;
-                tm.fwd(sm, L, d, a.dr, s, h, seq0);
+                tm.fwd(sm, L, d, dr, s, h, seq0);
                 MMX_UNROLL
                 for (int t = 0; t < (TC > 0 ? TC : T); ++t)
                     sm[L.bYt + (s * T + t) * PH + h] = tm.y[t];
@@ -543,14 +542,14 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
                 const float u = v + sm[L.cb1 + n];
                 sm[L.bU + m * PC + n] = u;
                 float gv = act_fwd<ACT>(u);
-                if (drop) gv *= dropout_scale(a.dr, d.site_base + 2, ((unsigned long long)seq0 * T + m) * ch + n);
+                if (drop) gv *= dropout_scale(dr, d.site_base + 2, ((unsigned long long)seq0 * T + m) * ch + n);
                 sm[L.bG + m * PC + n] = gv;
             });
         });
         ex.phase([&](int tid) {
             gemm_nt<4, 4>(tid, nthr, sm + L.bG, PC, V2, ldv2, nr, H, ch, [&](int m, int n, float v) {
                 float yv = v + sm[L.cb2 + n];
-                if (drop) yv *= dropout_scale(a.dr, d.site_base + 3, ((unsigned long long)seq0 * T + m) * H + n);
+                if (drop) yv *= dropout_scale(dr, d.site_base + 3, ((unsigned long long)seq0 * T + m) * H + n);
                 sm[L.bY2 + m * PH + n] = yv;
             });
         });
@@ -584,7 +583,7 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
                     if (d.use_max) { if ((float)h == sm[L.amax2 + r]) v += sm[L.ds2 + r]; }
                     else v = fmaf(sm[L.ds2 + r], invH, v);
                 }
-                if (drop) v *= dropout_scale(a.dr, d.site_base + 3, ((unsigned long long)seq0 * T + r) * H + h);
+                if (drop) v *= dropout_scale(dr, d.site_base + 3, ((unsigned long long)seq0 * T + r) * H + h);
                 sm[L.bY2 + r * PH + h] = v;
             }
         });
@@ -614,7 +613,7 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
             gemm_nn<4>(tid, nthr, sm + L.bY2, PH, V2, ldv2, nr, ch, H, [&](int m, int n, float v) {
                 float ga;
                 const float gp = act_fwd_grad<ACT>(sm[L.bU + m * PC + n], &ga);
-                if (drop) v *= dropout_scale(a.dr, d.site_base + 2, ((unsigned long long)seq0 * T + m) * ch + n);
+                if (drop) v *= dropout_scale(dr, d.site_base + 2, ((unsigned long long)seq0 * T + m) * ch + n);
                 sm[L.bU + m * PC + n] = v * gp;
             });
         });
@@ -702,7 +701,7 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
             MlpBwdRegs<WT>& rg = regs[tid];
             for (int p = tid; p < ns * H; p += nthr) {
                 const int s = p / H, h = p - s * H;
-                tm.fwd(sm, L, d, a.dr, s, h, seq0);
+                tm.fwd(sm, L, d, dr, s, h, seq0);
                 const unsigned long long pair = (unsigned long long)(seq0 + s) * H + h;
                 float dyt[TDim<TC>::cap];
                 MMX_UNROLL
@@ -715,9 +714,8 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
                             if (d.use_max) { if ((float)h == sm[L.amax1 + r]) v += sm[L.ds1 + r]; }
                             else v = fmaf(sm[L.ds1 + r], invH, v);
                         }
-                        if (drop) v *= dropout_scale(a.dr, d.site_base + 1, pair * T + t);
+                        if (drop) v *= dropout_scale(dr, d.site_base + 1, pair * T + t);
                         dyt[t] = v;
-                        rg.db2[t] += v;
                         sm[L.bYt + r * PH + h] = v;             // dYt, row-major  (A operand of dW2)
                         sm[L.bN1 + r * PH + h] = tm.n[t];       // N1, row-major   (B operand of dW1)
                     }
@@ -731,10 +729,9 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
                         MMX_UNROLL
                         for (int t = 0; t < (TC > 0 ? TC : T); ++t)
                             dg = fmaf(sm[L.tw2 + t * tok + k], dyt[t], dg);
-                        if (drop) dg *= dropout_scale(a.dr, d.site_base + 0, pair * tok + k);
+                        if (drop) dg *= dropout_scale(dr, d.site_base + 0, pair * tok + k);
                         float ga;
                         const float du = dg * act_fwd_grad<ACT>(tm.u[k], &ga);
-                        rg.db1[k] += du;
                         sm[L.tG + (s * tok + k) * PH + h] = tm.g[k];
                         sm[L.tdU + (s * tok + k) * PH + h] = du;
                         MMX_UNROLL
@@ -791,6 +788,20 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
                     }
                 }
             }
+            // token-MLP bias gradients: db1[k] = sum_{s,h} dU[(s,k)][h], db2[t] = sum_{s,h} dYt[(s,t)][h]
+            // (8 partial sums per output, combined with shared-memory atomics)
+            for (int i = tid; i < (tok + T) * 8; i += nthr) {
+                const int o = i >> 3, part = i & 7;
+                const bool is1 = o < tok;
+                const int rows_per_s = is1 ? tok : T, row_in_s = is1 ? o : o - tok;
+                const float* base = sm + (is1 ? L.tdU : L.bYt);
+                float sacc = 0.0f;
+                for (int s2 = 0; s2 < ns; ++s2) {
+                    const float* row = base + (s2 * rows_per_s + row_in_s) * PH;
+                    for (int h = part; h < H; h += 8) sacc += row[h];
+                }
+                smem_add(sm + (is1 ? L.a_tb1 + o : L.a_tb2 + (o - tok)), sacc);
+            }
             // LN1 backward, columns: dgamma1/dbeta1
             for (int h = tid; h < H; h += nthr) {
                 float sg = 0.0f, sb = 0.0f;
@@ -838,12 +849,8 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
             if (otile < w2_tiles) flush_acc4x4(rg.dW2, otile, w2_nt, a.g.tw2, tok, T, tok);
             if (otile < w1_tiles) flush_acc4x4(rg.dW1, otile, w1_nt, a.g.tw1, T, tok, T);
         }
-        MMX_UNROLL
-        for (int k = 0; k < (TOKC > 0 ? TOKC : tok); ++k)
-            red_add(a.g.tb1 + k, rg.db1[k]);
-        MMX_UNROLL
-        for (int t = 0; t < (TC > 0 ? TC : T); ++t)
-            red_add(a.g.tb2 + t, rg.db2[t]);
+        for (int k = tid; k < tok; k += nthr) red_add(a.g.tb1 + k, sm[L.a_tb1 + k]);
+        for (int t = tid; t < T; t += nthr) red_add(a.g.tb2 + t, sm[L.a_tb2 + t]);
         for (int h = tid; h < H; h += nthr) {
             red_add(a.g.ln1_g + h, sm[L.a_ln1g + h]); red_add(a.g.ln1_b + h, sm[L.a_ln1b + h]);
             red_add(a.g.ln2_g + h, sm[L.a_ln2g + h]); red_add(a.g.ln2_b + h, sm[L.a_ln2b + h]);

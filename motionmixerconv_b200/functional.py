@@ -95,9 +95,9 @@ def mlp_block_table(tensors):
     return t
 
 
-def mlp_block_desc(B, T, H, tok, ch, se_hidden, act, use_se, use_max, training, block_index, p, seed, step):
+def mlp_block_desc(B, T, H, tok, ch, se_hidden, act, use_se, use_max, training, block_index, p, seed, step, step_dev=None):
     return L.MmxMlpBlockDesc(B, T, H, tok, ch, se_hidden, L.MMX_ACT[act], int(use_se), int(use_max), int(training),
-                             block_index, L.MmxDropout(float(p), int(seed), int(step)))
+                             block_index, L.MmxDropout(float(p), int(seed), int(step), step_dev))
 
 
 class _MlpBlock(torch.autograd.Function):

@@ -1,0 +1,325 @@
+"""The training step as one replayable unit: forward -> MPJPE -> backward -> (all-reduce) -> Adam.
+
+``TrainStep`` is the fast path for the loop body of ``h36m/train_mixer_h36m.py:110-195``
+(``zero_grad; pred = model(x); loss = mpjpe_error(pred, gt); loss.backward(); optimizer.step()``):
+
+* every parameter of the model becomes a view into ONE flat fp32 buffer, gradients / Adam moments
+  live in matching flat buffers (``state_dict`` is unaffected: the nn.Parameters keep their names
+  and shapes, only their storage moves);
+* the kernels are called straight through the C ABI on preallocated activations — no autograd
+  graph, no per-op allocation — and the whole step is captured in a CUDA graph;
+* data parallelism: one process per GPU, the batch is sharded by the caller, and ONE
+  ``all_reduce(SUM)`` over the flat gradient bucket (NCCL over NVLink) sits between backward and
+  the fused Adam, which folds the ``1/world_size`` in.  Replicated optimizer state.
+
+The autograd path (``model(x)`` + any torch optimizer) stays available and produces the same numbers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import functional as F_
+from .functional import _p
+
+
+class FlatBuffers:
+    """Flat param / grad / exp_avg / exp_avg_sq buffers; parameters are re-pointed to views."""
+
+    def __init__(self, model):
+        params = []
+        seen = set()
+        for p in model.parameters():
+            if id(p) not in seen and p.requires_grad:
+                seen.add(id(p))
+                params.append(p)
+        if not params:
+            raise ValueError("model has no trainable parameters")
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("TrainStep needs the model on a CUDA device (model.to('cuda') first)")
+        self.params = params
+        self.offsets = []
+        o = 0
+        for p in params:
+            self.offsets.append(o)
+            o += (p.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
+        self.numel = o
+        self.p = torch.zeros(o, dtype=torch.float32, device=dev)
+        self.g = torch.zeros_like(self.p)
+        self.m = torch.zeros_like(self.p)
+        self.v = torch.zeros_like(self.p)
+        self.grad_views = {}
+        with torch.no_grad():
+            for p, off in zip(params, self.offsets):
+                view = self.p[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                self.grad_views[id(p)] = self.g[off:off + p.numel()].view(p.shape)
+
+    def grad_of(self, p):
+        return None if p is None else self.grad_views[id(p)]
+
+    def attach_grads(self):
+        """Expose the flat gradient buffer through ``param.grad`` (for clip_grad_norm_, inspection)."""
+        for p in self.params:
+            p.grad = self.grad_views[id(p)]
+
+
+class _MlpMixerPlan:
+    """Pointer tables + static activations for one (model, batch size)."""
+
+    def __init__(self, model, flat, B, dropout_step_dev):
+        from .mlp_mixer import MlpMixer
+        assert isinstance(model, MlpMixer)
+        self.model, self.B = model, B
+        dev = flat.p.device
+        T, H, D, To = model.seq_len, model.hidden_dim, model.input_size, model.pred_len
+        self.x = torch.zeros(B, T, D, device=dev)
+        self.acts = [torch.empty(B, T, H, device=dev) for _ in range(model.num_blocks + 1)]
+        self.pred = torch.empty(B, To, model.num_classes, device=dev)
+        self.dpred = torch.empty_like(self.pred)
+        self.dact = [torch.empty(B, T, H, device=dev) for _ in range(2)]
+        self.step_dev = dropout_step_dev
+        self.blocks = []
+        for mb in model.Mixer_Block:
+            if mb.regularization == -1.0:
+                raise NotImplementedError("TrainStep: BatchNorm (regularization=-1) MixerBlocks are not built yet")
+            kp = mb.kernel_params()
+            self.blocks.append((mb, F_.mlp_block_table(kp), F_.mlp_block_table([flat.grad_of(q) for q in kp])))
+        hp = [model.LN.weight, model.LN.bias, model.conv_out.weight, model.conv_out.bias, model.fc_out.weight, model.fc_out.bias]
+        self.head_w = F_.mlp_head_table(hp)
+        self.head_g = F_.mlp_head_table([flat.grad_of(q) for q in hp])
+        self.head_desc = L.MmxMlpHeadDesc(B, T, To, H, model.num_classes)
+        self.conv_w, self.conv_b = model.conv.weight, model.conv.bias
+        self.conv_gw, self.conv_gb = flat.grad_of(model.conv.weight), flat.grad_of(model.conv.bias)
+        self.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        self.n_launches_fwd = 2 + model.num_blocks
+        self.n_launches_bwd = 2 + model.num_blocks
+
+    def _desc(self, mb, training):
+        m = mb.meta(self.seed, 0)
+        T, H = self.model.seq_len, self.model.hidden_dim
+        return F_.mlp_block_desc(self.B, T, H, *m[:6], training, *m[7:], step_dev=_p(self.step_dev) if training else None)
+
+    def forward(self, lib, st, training):
+        md = self.model
+        T, H, D = md.seq_len, md.hidden_dim, md.input_size
+        L.check(lib, lib.mmx_linear_fwd(self.B * T, D, H, _p(self.x), _p(self.conv_w), _p(self.conv_b), _p(self.acts[0]), st), "mmx_linear_fwd")
+        for i, (mb, tw, _) in enumerate(self.blocks):
+            d = self._desc(mb, training)
+            L.check(lib, lib.mmx_mlp_block_fwd(C.byref(d), C.byref(tw), _p(self.acts[i]), _p(self.acts[i + 1]), st), "mmx_mlp_block_fwd")
+        L.check(lib, lib.mmx_mlp_head_fwd(C.byref(self.head_desc), C.byref(self.head_w), _p(self.acts[-1]), _p(self.pred), st), "mmx_mlp_head_fwd")
+        return self.pred
+
+    def backward(self, lib, st):
+        md = self.model
+        T, H, D = md.seq_len, md.hidden_dim, md.input_size
+        cur = self.dact[0]
+        L.check(lib, lib.mmx_mlp_head_bwd(C.byref(self.head_desc), C.byref(self.head_w), C.byref(self.head_g),
+                                          _p(self.acts[-1]), _p(self.dpred), _p(cur), st), "mmx_mlp_head_bwd")
+        for i in reversed(range(len(self.blocks))):
+            mb, tw, tg = self.blocks[i]
+            nxt = self.dact[1] if cur is self.dact[0] else self.dact[0]
+            d = self._desc(mb, True)
+            L.check(lib, lib.mmx_mlp_block_bwd(C.byref(d), C.byref(tw), C.byref(tg), _p(self.acts[i]), _p(cur), _p(nxt), st), "mmx_mlp_block_bwd")
+            cur = nxt
+        L.check(lib, lib.mmx_linear_bwd(self.B * T, D, H, _p(self.x), _p(self.conv_w), _p(cur), _p(self.conv_gw), _p(self.conv_gb), None, st), "mmx_linear_bwd")
+
+
+def _make_plan(model, flat, B, step_dev):
+    from .mlp_mixer import MlpMixer
+    if isinstance(model, MlpMixer):
+        return _MlpMixerPlan(model, flat, B, step_dev)
+    try:
+        from .conv_mixer_model import ConvMixer, _ConvMixerPlan
+    except ImportError:
+        ConvMixer = None
+    if ConvMixer is not None and isinstance(model, ConvMixer):
+        return _ConvMixerPlan(model, flat, B, step_dev)
+    raise TypeError("TrainStep supports motionmixerconv_b200 MlpMixer / ConvMixer, got %s" % type(model).__name__)
+
+
+class TrainStep:
+    """``loss = step(x, gt)`` == one iteration of the reference training loop, fused.
+
+    Args mirror the reference call sites: ``lr`` / ``weight_decay`` as in
+    ``optim.Adam(model.parameters(), lr=args.lr, weight_decay=1e-05)`` (train_mixer_h36m.py:63);
+    ``loss_scale`` is the ``*1000`` of amass/train_mixer_amass.py:92.  ``process_group``: a
+    torch.distributed group for batch-sharded data parallelism (None = single GPU).
+    """
+
+    def __init__(self, model, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, loss_scale=1.0,
+                 process_group=None, use_cuda_graph=True):
+        self.model = model
+        self.lib = L.load()
+        self.flat = FlatBuffers(model)
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.loss_scale = loss_scale
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if process_group is not None else 1
+        self.use_graph = use_cuda_graph
+        dev = self.flat.p.device
+        self.device = dev
+        # optimiser clock and hyper-parameters live on the device (mmx_adam_advance): nothing is
+        # written from the host per step, so the step is replayable from a CUDA graph
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, 1.0, 1.0, 1.0 / self.world],
+                                  dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.plan = None
+        self.gt = None
+        self.graph_a = self.graph_b = None
+        self.kernel_launches_per_step = 0
+
+    # ---- pieces -------------------------------------------------------------------------------
+    def _fwd_bwd(self):
+        lib, pl = self.lib, self.plan
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.flat.g.zero_()
+        self.loss_sum.zero_()
+        pred = pl.forward(lib, st, training=self.model.training)
+        n_joints = pred.numel() // 3
+        L.check(lib, lib.mmx_mpjpe_fwd_bwd(_p(pred), _p(self.gt), _p(pl.dpred), _p(self.loss_sum), n_joints,
+                                           float(self.loss_scale), st), "mmx_mpjpe_fwd_bwd")
+        pl.backward(lib, st)
+
+    def _adam(self):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        f = self.flat
+        L.check(self.lib, self.lib.mmx_adam_advance(_p(self.hyper), _p(self.step_dev), st), "mmx_adam_advance")
+        L.check(self.lib, self.lib.mmx_adam_step(_p(f.p), _p(f.g), _p(f.m), _p(f.v), f.numel, _p(self.hyper), st), "mmx_adam_step")
+
+    def _prepare(self, x, gt):
+        B = x.shape[0]
+        if self.plan is None or self.plan.B != B:
+            self.plan = _make_plan(self.model, self.flat, B, self.step_dev)
+            self.gt = torch.empty_like(gt, device=self.device)
+            self.graph_a = self.graph_b = None
+            self.kernel_launches_per_step = self.plan.n_launches_fwd + self.plan.n_launches_bwd + 3  # + mpjpe, adam_advance, adam
+
+    def set_lr(self, lr):
+        """Change the learning rate (e.g. from a MultiStepLR schedule, train_mixer_h36m.py:65-67,249)."""
+        if lr != self.lr:
+            self.lr = lr
+            self.hyper[0:1].fill_(lr)
+
+    @property
+    def steps_done(self):
+        return int(self.step_dev.item())
+
+    # ---- public -------------------------------------------------------------------------------
+    def step(self, x, gt):
+        """x: [B,T,D], gt: [B,To,D] (CUDA or pinned host tensors).  Returns the loss as a 0-d CUDA tensor
+        (mean MPJPE of THIS rank's shard times ``loss_scale``); no host synchronisation."""
+        self._prepare(x, gt)
+        pl = self.plan
+        pl.x.copy_(x, non_blocking=True)
+        self.gt.copy_(gt, non_blocking=True)
+        if not self.use_graph:
+            self._fwd_bwd()
+            if self.world > 1:
+                dist.all_reduce(self.flat.g, group=self.pg)
+            self._adam()
+        else:
+            if self.graph_a is None:
+                self._capture()
+            self.graph_a.replay()
+            if self.world > 1:
+                dist.all_reduce(self.flat.g, group=self.pg)
+            self.graph_b.replay()
+        n_joints = pl.pred.numel() // 3
+        return (self.loss_sum * (float(self.loss_scale) / n_joints)).reshape(())
+
+    def _capture(self):
+        # warm-up on a side stream (first launches set kernel attributes), then capture
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        saved = [b.clone() for b in (self.flat.p, self.flat.m, self.flat.v, self.hyper, self.step_dev)]
+        with torch.cuda.stream(s):
+            self._fwd_bwd()
+            self._adam()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        with torch.no_grad():
+            for b, sv in zip((self.flat.p, self.flat.m, self.flat.v, self.hyper, self.step_dev), saved):
+                b.copy_(sv)
+        self.graph_a = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_a):
+            self._fwd_bwd()
+        self.graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_b):
+            self._adam()
+
+    @torch.no_grad()
+    def predict(self, x):
+        """Inference forward through the same preallocated plan (eval semantics: no dropout)."""
+        self._prepare(x, torch.empty(x.shape[0], 1, 3, device=self.device) if self.gt is None else self.gt)
+        self.plan.x.copy_(x, non_blocking=True)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return self.plan.forward(self.lib, st, training=False)
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam`` (coupled L2, no amsgrad) as ONE multi-tensor kernel over flat buffers.
+
+    Drop-in for ``optim.Adam(model.parameters(), lr=..., weight_decay=1e-05)``
+    (train_mixer_h36m.py:63): ``lr`` is read from ``param_groups`` at every step, so
+    ``MultiStepLR`` (:65-67) keeps working.  Parameters are re-pointed to views of a flat buffer on
+    the first step; gradients produced by autograd are gathered into the flat gradient buffer.
+    """
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._flat = {}
+
+    def _flatten(self, gi, group):
+        ps = [p for p in group["params"] if p.requires_grad]
+        dev = ps[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedAdam needs CUDA parameters")
+        offs, o = [], 0
+        for p in ps:
+            offs.append(o)
+            o += (p.numel() + 3) // 4 * 4
+        flat = torch.zeros(o, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, off in zip(ps, offs):
+                v = flat[off:off + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+        st = dict(ps=ps, offs=offs, p=flat, g=torch.zeros_like(flat), m=torch.zeros_like(flat), v=torch.zeros_like(flat),
+                  hyper=torch.tensor([group["lr"], group["betas"][0], group["betas"][1], group["eps"], group["weight_decay"], 1.0, 1.0, 1.0],
+                                     dtype=torch.float32, device=dev),
+                  step=torch.zeros(1, dtype=torch.int32, device=dev), lr=group["lr"])
+        self._flat[gi] = st
+        return st
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = L.load()
+        for gi, group in enumerate(self.param_groups):
+            st = self._flat.get(gi) or self._flatten(gi, group)
+            for p, off in zip(st["ps"], st["offs"]):
+                gv = st["g"][off:off + p.numel()]
+                if p.grad is None:
+                    gv.zero_()
+                else:
+                    gv.copy_(p.grad.reshape(-1))
+            if group["lr"] != st["lr"]:
+                st["lr"] = group["lr"]
+                st["hyper"][0:1].fill_(group["lr"])
+            with torch.cuda.device(st["p"].device):
+                stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                L.check(lib, lib.mmx_adam_advance(_p(st["hyper"]), _p(st["step"]), stream), "mmx_adam_advance")
+                L.check(lib, lib.mmx_adam_step(_p(st["p"]), _p(st["g"]), _p(st["m"]), _p(st["v"]), st["p"].numel(),
+                                               _p(st["hyper"]), stream), "mmx_adam_step")
+        return loss

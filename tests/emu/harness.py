@@ -58,7 +58,7 @@ def call(name, *args):
 
 
 def dropout_struct(p=0.0, seed=0, step=0):
-    return L.MmxDropout(p, seed, step)
+    return L.MmxDropout(p, seed, step, None)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -77,3 +77,33 @@ def test_fp64_noise_floor():
     p32 = make_oracle(g, np.float32).forward(g.x)
     p64 = make_oracle(g, np.float64).forward(g.x)
     assert rel_err(p32, p64) < 5e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# the torch-CPU functional port (oracle/mixer_torch.py) that bench.py times as the CPU baseline
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", golden_cases())
+def test_torch_port_matches_reference(case):
+    import torch
+    from oracle import mixer_torch as MT
+    g = Golden(case)
+    p = {k: torch.from_numpy(np.array(v)) for k, v in g.params.items()}
+    for k in p:
+        if MT.is_trainable(k) and p[k].dtype.is_floating_point:
+            p[k].requires_grad_(True)
+    fwd = MT.mlpmixer_forward if g.family == "mlp" else MT.convmixer_forward
+    x = torch.from_numpy(g.x).requires_grad_(True)
+    pred = fwd(p, g.cfg, x, training=True)
+    loss = MT.mpjpe_error(pred, torch.from_numpy(g.gt))
+    loss.backward()
+    check_close("pred", pred.detach().numpy(), g.pred, rtol=1e-6)
+    assert abs(float(loss) - g.loss) <= 1e-6 * abs(g.loss)
+    floor = 1e-6 * grad_scale(g.grads)
+    _, _, _, grads64, _ = run(g, np.float64)     # summation order differs with the thread count: noise-aware
+    for k, want in g.grads.items():
+        check_close("grad " + k, p[k].grad.numpy(), want, grads64[k], rtol=1e-5, atol=floor)
+    # the layout produced without the reference (bench.py on the GPU box) has the same keys/shapes
+    rp = MT.random_params(g.family, g.cfg)
+    assert list(rp.keys()) == list(g.params.keys())
+    for k in rp:
+        assert tuple(rp[k].shape) == tuple(g.params[k].shape), k

@@ -13,7 +13,7 @@ from motionmixerconv_b200 import functional as F_
 PEAK = 6539.2
 
 
-def timeit(fn, iters=20, warm=5):
+def timeit(fn, iters=int(os.environ.get('ITERS', 20)), warm=int(os.environ.get('WARM', 5))):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -40,7 +40,7 @@ def main():
     lib = L.load()
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     out = {}
-    for p_drop in (0.0, 0.1):
+    for p_drop in [float(v) for v in os.environ.get('PDROP', '0.0,0.1').split(',')]:
         desc = F_.mlp_block_desc(B, T, H, tok, ch, 1, act, True, False, True, 0, p_drop, 1234, 0)
         tw, tg = F_.mlp_block_table(params), F_.mlp_block_table(grads)
         tf = timeit(lambda: L.check(lib, lib.mmx_mlp_block_fwd(C.byref(desc), C.byref(tw), x.data_ptr(), y.data_ptr(), st), "fwd"))
