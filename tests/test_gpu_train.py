@@ -53,10 +53,12 @@ def test_mpjpe_after_200_steps_within_0p1mm_of_oracle():
     orc = O.MlpMixerOracle(g.cfg, g.params)
     want = O.train_steps(orc, x, gt, 200)[-1]
     assert abs(ours - want) < 0.1, (ours, want)           # mm
-    assert want < 0.9 * O.train_steps(O.MlpMixerOracle(g.cfg, g.params), x, gt, 1)[0]   # it did train
+    assert want < O.train_steps(O.MlpMixerOracle(g.cfg, g.params), x, gt, 1)[0] - 5.0   # it did train (mm)
 
 
 def test_fused_adam_matches_torch_adam():
+    """Same gradients into torch.optim.Adam and FusedAdam (the gradients of model A are copied into model B, so the
+    comparison is of the optimisers alone and not of the atomics' summation order), with a MultiStepLR on both."""
     from motionmixerconv_b200.functional import mpjpe_error
     from motionmixerconv_b200.train import FusedAdam
     g = Golden("mlp_odd_nose")
@@ -67,14 +69,19 @@ def test_fused_adam_matches_torch_adam():
     sched = torch.optim.lr_scheduler.MultiStepLR(ob, milestones=[2], gamma=0.1)
     scheda = torch.optim.lr_scheduler.MultiStepLR(oa, milestones=[2], gamma=0.1)
     for _ in range(4):
-        for m, o in ((ma, oa), (mb, ob)):
-            o.zero_grad()
-            mpjpe_error(m(x), gt).backward()
-            o.step()
+        oa.zero_grad()
+        mpjpe_error(ma(x), gt).backward()
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            pb.grad = pa.grad.clone()
+        oa.step()
+        ob.step()
         sched.step()
         scheda.step()
+        with torch.no_grad():                      # keep the two models on the same trajectory
+            worst = max((pa - pb).abs().max().item() for pa, pb in zip(ma.parameters(), mb.parameters()))
+        assert worst <= 2e-6, worst                # one step moves a weight by <= lr = 1e-3
     for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
-        assert (pa - pb).abs().max().item() <= 2e-5, k
+        assert (pa - pb).abs().max().item() <= 5e-6, k
 
 
 def test_dropout_training_mode():
