@@ -94,6 +94,72 @@ int mmx_mlp_head_fwd(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const f
 int mmx_mlp_head_bwd(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const MmxMlpHeadParams* grads,
                      const float* x, const float* dout, float* dx, void* stream);
 
+/* ---------------- ConvMixer (h36m/conv_mixer_model.py, conv_mixer/encoding/positional_encoder.py) ---------------- */
+
+/* One half of a ConvMixerBlock (conv_mixer_model.py:279-284 resp. :287-292):
+ *     y = x + SE(reg(act(conv2d(LN(x)))))        x, y: [B, C, T, E]
+ * conv: C -> C channels, kernel (kt, kp) over (time, embedding), stride 1, zero padding pad_t rows on top
+ * and pad_p columns on the left (bottom / right = k-1-pad: PyTorch 'same' puts the surplus there; an explicit
+ * padding tuple must satisfy 2*pad == k-1, otherwise the reference's residual add fails as well). */
+typedef struct {
+    float *ln_w, *ln_b;     /* LN1 / LN2 .weight, .bias                         [E]            */
+    float *conv_w, *conv_b; /* conv1 / conv2 .conv.weight, .conv.bias           [C,C,kt,kp],[C]*/
+    float *se_w1, *se_w2;   /* se.excitationBlock.0.weight [T/r,T], .2.weight [T,T/r]; null if !use_se */
+} MmxConvHalfParams;
+
+typedef struct {
+    int B, C, T, E;         /* batch, conv_nChan, in_nTP, dimPosEmb */
+    int kt, kp, pad_t, pad_p;
+    int se_hidden;          /* T / r_se */
+    int act;                /* MMX_ACT_* */
+    int use_se, use_max_pooling;
+    int training;
+    int site;               /* dropout site of this half: 2*block_index + (0|1) */
+    MmxDropout dropout;
+} MmxConvHalfDesc;
+
+int mmx_conv_half_fwd(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, const float* x, float* y, void* stream);
+/* dx written; grads accumulated.  The forward is recomputed from x. */
+int mmx_conv_half_bwd(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, const MmxConvHalfParams* grads,
+                      const float* x, const float* dy, float* dx, void* stream);
+
+/* mode_conv="once": the second half of ConvMixerBlock.forward degenerates to y = x + se(x)  (or 2x without SE),
+ * conv_mixer_model.py:259-263,287-292.  x, y: [B,C,T,E]; se weights may be null when !use_se. */
+int mmx_se_tail_fwd(int B, int C, int T, int E, int se_hidden, int use_se, int use_max_pooling,
+                    const float* se_w1, const float* se_w2, const float* x, float* y, void* stream);
+int mmx_se_tail_bwd(int B, int C, int T, int E, int se_hidden, int use_se, int use_max_pooling,
+                    const float* se_w1, const float* se_w2, float* g_se_w1, float* g_se_w2,
+                    const float* x, const float* dy, float* dx, void* stream);
+
+/* PoseEncoder.forward (positional_encoder.py:79-97): optional harmonic embedding (sin/cos of x*frequencies,
+ * the argument formed by ONE fp32 multiply) -> embed_mlp -> channelUpscaling.
+ * x: [B,T,D];  m: [B*T,E] = embed_mlp output (saved for the backward);  y: [B,C,T,E]. */
+typedef struct {
+    float* freq;            /* encoder.frequencies [n_harmonic] (null when n_harmonic <= 0)                 */
+    float *w, *b;           /* encoder.embed_mlp.weight [E, K], .bias [E];  K = n_harmonic>0 ? 2*n_harmonic*D : D */
+    float *wc, *bc;         /* encoder.channelUpscaling.weight [C,1], .bias [C]                              */
+} MmxEncoderParams;
+typedef struct { int B, T, D, E, C, n_harmonic; } MmxEncoderDesc;
+
+int mmx_pose_encoder_fwd(const MmxEncoderDesc* d, const MmxEncoderParams* w, const float* x, float* m, float* y, void* stream);
+/* grads accumulated (grads->freq ignored).  dm_ws: caller-provided workspace [B*T,E].  dx: nullable; written. */
+int mmx_pose_encoder_bwd(const MmxEncoderDesc* d, const MmxEncoderParams* w, const MmxEncoderParams* grads,
+                         const float* x, const float* m, const float* dy, float* dm_ws, float* dx, void* stream);
+
+/* ConvMixer head (conv_mixer_model.py:455-463): LN -> conv_out (T -> To) -> project_channels (C -> 1) -> GELU -> fc_out.
+ * y: [B,C,T,E] -> out: [B,To,D]. */
+typedef struct {
+    float *ln_w, *ln_b;     /* LN.weight, LN.bias                              [E]             */
+    float *wt, *bt;         /* conv_out.weight [To,T,1,1], conv_out.bias [To]                  */
+    float *wp, *bp;         /* project_channels.weight [1,C,1,1], .bias [1]                    */
+    float *wf, *bf;         /* fc_out.weight [D,E], fc_out.bias [D]                            */
+} MmxConvHeadParams;
+typedef struct { int B, C, T, To, E, D; } MmxConvHeadDesc;
+
+int mmx_conv_head_fwd(const MmxConvHeadDesc* d, const MmxConvHeadParams* w, const float* y, float* out, void* stream);
+int mmx_conv_head_bwd(const MmxConvHeadDesc* d, const MmxConvHeadParams* w, const MmxConvHeadParams* grads,
+                      const float* y, const float* dout, float* dy, void* stream);
+
 /* ---------------- loss / optimiser ---------------- */
 
 /* MPJPE (utils_mixer.py:48-53): *loss_sum += sum_joints ||gt - pred||_2 (caller zeroes it; mean =
@@ -102,7 +168,8 @@ int mmx_mpjpe_fwd_bwd(const float* pred, const float* gt, float* dpred, float* l
                       float gscale, void* stream);
 
 /* torch.optim.Adam (coupled L2) on flat buffers — train_mixer_h36m.py:63,193.
- * hyper (DEVICE, 8 floats): lr, beta1, beta2, eps, weight_decay, 1-beta1^t, sqrt(1-beta2^t), grad_scale. */
+ * hyper (DEVICE, 10 floats): lr, beta1, beta2, eps, weight_decay, 1-beta1^t, sqrt(1-beta2^t), grad_scale,
+ * 1-beta1, 1-beta2 (the last two rounded once from double, as PyTorch does). */
 int mmx_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* hyper, void* stream);
 /* Device-side optimiser clock: ++*step (DEVICE uint32, also the dropout step_dev); hyper[5], hyper[6] are
  * recomputed from hyper[1], hyper[2] and the new step.  Lets a CUDA graph replay a whole training step. */

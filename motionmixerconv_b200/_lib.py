@@ -41,18 +41,23 @@ class MmxMlpHeadDesc(C.Structure):
     _fields_ = [("B", C.c_int), ("T", C.c_int), ("To", C.c_int), ("H", C.c_int), ("D", C.c_int)]
 
 
-class MmxConvBlockParams(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in (
-        "ln1_w", "ln1_b", "conv1_w", "conv1_b", "ln2_w", "ln2_b", "conv2_w", "conv2_b", "se_w1", "se_w2")]
+class MmxConvHalfParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln_w", "ln_b", "conv_w", "conv_b", "se_w1", "se_w2")]
 
 
-class MmxConvBlockDesc(C.Structure):
+class MmxConvHalfDesc(C.Structure):
     _fields_ = [("B", C.c_int), ("C", C.c_int), ("T", C.c_int), ("E", C.c_int),
-                ("k1t", C.c_int), ("k1p", C.c_int), ("p1t", C.c_int), ("p1p", C.c_int),
-                ("k2t", C.c_int), ("k2p", C.c_int), ("p2t", C.c_int), ("p2p", C.c_int),
-                ("twice", C.c_int), ("se_hidden", C.c_int), ("act", C.c_int), ("use_se", C.c_int),
-                ("use_max_pooling", C.c_int), ("training", C.c_int), ("block_index", C.c_int),
-                ("dropout", MmxDropout)]
+                ("kt", C.c_int), ("kp", C.c_int), ("pad_t", C.c_int), ("pad_p", C.c_int),
+                ("se_hidden", C.c_int), ("act", C.c_int), ("use_se", C.c_int), ("use_max_pooling", C.c_int),
+                ("training", C.c_int), ("site", C.c_int), ("dropout", MmxDropout)]
+
+
+class MmxEncoderParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("freq", "w", "b", "wc", "bc")]
+
+
+class MmxEncoderDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("T", C.c_int), ("D", C.c_int), ("E", C.c_int), ("C", C.c_int), ("n_harmonic", C.c_int)]
 
 
 class MmxConvHeadParams(C.Structure):
@@ -61,14 +66,6 @@ class MmxConvHeadParams(C.Structure):
 
 class MmxConvHeadDesc(C.Structure):
     _fields_ = [("B", C.c_int), ("C", C.c_int), ("T", C.c_int), ("To", C.c_int), ("E", C.c_int), ("D", C.c_int)]
-
-
-class MmxEncoderDesc(C.Structure):
-    _fields_ = [("B", C.c_int), ("T", C.c_int), ("D", C.c_int), ("E", C.c_int), ("C", C.c_int), ("n_harmonic", C.c_int)]
-
-
-class MmxEncoderParams(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("freq", "w", "b", "wc", "bc")]
 
 
 # name -> (restype, argtypes).  Everything declared in include/mmx.h must appear here
@@ -85,6 +82,17 @@ SIGNATURES = {
     "mmx_mlp_head_fwd": (C.c_int, [C.POINTER(MmxMlpHeadDesc), C.POINTER(MmxMlpHeadParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_mlp_head_bwd": (C.c_int, [C.POINTER(MmxMlpHeadDesc), C.POINTER(MmxMlpHeadParams), C.POINTER(MmxMlpHeadParams),
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_conv_half_fwd": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_conv_half_bwd": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams), C.POINTER(MmxConvHalfParams),
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_se_tail_fwd": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 5),
+    "mmx_se_tail_bwd": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 8),
+    "mmx_pose_encoder_fwd": (C.c_int, [C.POINTER(MmxEncoderDesc), C.POINTER(MmxEncoderParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_pose_encoder_bwd": (C.c_int, [C.POINTER(MmxEncoderDesc), C.POINTER(MmxEncoderParams), C.POINTER(MmxEncoderParams),
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_conv_head_fwd": (C.c_int, [C.POINTER(MmxConvHeadDesc), C.POINTER(MmxConvHeadParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_conv_head_bwd": (C.c_int, [C.POINTER(MmxConvHeadDesc), C.POINTER(MmxConvHeadParams), C.POINTER(MmxConvHeadParams),
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_mpjpe_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p]),
     "mmx_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "mmx_adam_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1,0 +1,26 @@
+// mmx_conv_half_bwd: fused ConvMixerBlock-half backward (include/mmx.h).
+#define MMX_CONV_CP 1
+#include "mmx_api_conv_bwd.inl"
+
+int mmx_conv_bwd_launch_cp2(const mmx::ConvHalfBwdArgs& a, int act, int grid, size_t smem, void* stream);
+int mmx_conv_bwd_launch_cp4(const mmx::ConvHalfBwdArgs& a, int act, int grid, size_t smem, void* stream);
+int mmx_conv_bwd_launch_cp8(const mmx::ConvHalfBwdArgs& a, int act, int grid, size_t smem, void* stream);
+
+extern "C" int mmx_conv_half_bwd(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, const MmxConvHalfParams* grads,
+                                 const float* x, const float* dy, float* dx, void* stream) {
+    if (!x || !dy || !dx) return fail(MMX_E_INVALID, "mmx_conv_half_bwd: null tensor");
+    ConvHalfBwdArgs a;
+    size_t smem; int grid;
+    int rc = plan_conv_half(d, true, &a.d, &smem, &grid);
+    if (rc) return rc;
+    if ((rc = check_conv_params(w, d->use_se, "mmx_conv_half_bwd"))) return rc;
+    if ((rc = check_conv_params(grads, d->use_se, "mmx_conv_half_bwd(grads)"))) return rc;
+    a.dr = make_dropout(d->dropout, d->training);
+    a.w = to_cw(w); a.g = to_cw(grads); a.x = x; a.dy = dy; a.dx = dx;
+    switch (conv_cp(d->C)) {
+        case 1: return mmx_conv_bwd_launch_cp1(a, d->act, grid, smem, stream);
+        case 2: return mmx_conv_bwd_launch_cp2(a, d->act, grid, smem, stream);
+        case 4: return mmx_conv_bwd_launch_cp4(a, d->act, grid, smem, stream);
+        default: return mmx_conv_bwd_launch_cp8(a, d->act, grid, smem, stream);
+    }
+}

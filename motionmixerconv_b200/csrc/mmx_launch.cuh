@@ -114,4 +114,17 @@ static inline Dropout make_dropout(const MmxDropout& s, int training) {
 
 constexpr int kThreads = 256;
 
+// zero a device buffer on the stream (memset node: legal inside CUDA-graph capture)
+static inline int zero_async(void* p, size_t bytes, void* stream) {
+#if defined(MMX_HOST_EMU)
+    (void)stream;
+    memset(p, 0, bytes);
+    return MMX_OK;
+#else
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(MMX_E_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return MMX_OK;
+#endif
+}
+
 }  // namespace mmx

@@ -53,14 +53,15 @@ MMX_D void mpjpe_body(Exec& ex, const MpjpeArgs& a) {
 //   p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
 // Hyper-parameters come from a small DEVICE array so the launch can sit inside a CUDA graph
 // while lr / bias corrections change every step:
-//   hp = { lr, beta1, beta2, eps, weight_decay, 1-beta1^t, sqrt(1-beta2^t), gscale }
+//   hp = { lr, beta1, beta2, eps, weight_decay, 1-beta1^t, sqrt(1-beta2^t), gscale, 1-beta1, 1-beta2 }
+// (1-beta computed by the host in double and rounded once, as torch.optim.Adam does: 1.0f-0.999f != fl32(0.001))
 struct AdamArgs { float *p, *m, *v; const float* g; const float* hp; long long n; };
 
 MMX_D void adam_body(Exec& ex, const AdamArgs& a) {
     const int nthr = ex.nthr;
     ex.phase([&](int tid) {
         const float lr = a.hp[0], b1 = a.hp[1], b2 = a.hp[2], eps = a.hp[3], wd = a.hp[4];
-        const float bc1 = a.hp[5], bc2s = a.hp[6], gs = a.hp[7];
+        const float bc1 = a.hp[5], bc2s = a.hp[6], gs = a.hp[7], omb1 = a.hp[8], omb2 = a.hp[9];
         const float step = lr / bc1;
         const long long n4 = a.n >> 2;
         for (long long i = (long long)ex.bid * nthr + tid; i < n4; i += (long long)ex.nblk * nthr) {
@@ -69,8 +70,8 @@ MMX_D void adam_body(Exec& ex, const AdamArgs& a) {
             MMX_UNROLL
             for (int k = 0; k < 4; ++k) {
                 const float gr = fmaf(wd, pp[k], gs * gg[k]);
-                mm[k] = mm[k] + (gr - mm[k]) * (1.0f - b1);
-                vv[k] = fmaf(vv[k], b2, (1.0f - b2) * gr * gr);
+                mm[k] = mm[k] + (gr - mm[k]) * omb1;
+                vv[k] = fmaf(vv[k], b2, omb2 * gr * gr);
                 pp[k] -= step * (mm[k] / (sqrtf(vv[k]) / bc2s + eps));
             }
             st4(a.p + 4 * i, make_f4(pp[0], pp[1], pp[2], pp[3]));
@@ -80,8 +81,8 @@ MMX_D void adam_body(Exec& ex, const AdamArgs& a) {
         if (ex.bid == 0)
             for (long long i = 4 * n4 + tid; i < a.n; i += nthr) {
                 const float gr = fmaf(wd, a.p[i], gs * a.g[i]);
-                const float m = a.m[i] + (gr - a.m[i]) * (1.0f - b1);
-                const float v = fmaf(a.v[i], b2, (1.0f - b2) * gr * gr);
+                const float m = a.m[i] + (gr - a.m[i]) * omb1;
+                const float v = fmaf(a.v[i], b2, omb2 * gr * gr);
                 a.m[i] = m; a.v[i] = v;
                 a.p[i] -= step * (m / (sqrtf(v) / bc2s + eps));
             }

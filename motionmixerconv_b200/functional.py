@@ -8,6 +8,7 @@ takes the stream explicitly, and we re-enter the tensor's device before every ca
 from __future__ import annotations
 
 import ctypes as C
+import ctypes as C_   # (the conv wrappers use C for the channel count)
 
 import torch
 
@@ -208,3 +209,186 @@ class _Mpjpe(torch.autograd.Function):
 def mpjpe_error(batch_pred, batch_gt):
     """Drop-in for ``h36m.utils.utils_mixer.mpjpe_error`` (one fused kernel: loss + dL/dpred)."""
     return _Mpjpe.apply(batch_pred, batch_gt)
+
+
+# ------------------------------------------------------------------------------------------------
+# ConvMixer (conv_mixer_model.py, positional_encoder.py)
+# ------------------------------------------------------------------------------------------------
+def conv_half_table(tensors):
+    """tensors: (ln_w, ln_b, conv_w, conv_b, se_w1, se_w2) — the order of ``MmxConvHalfParams``."""
+    t = L.MmxConvHalfParams()
+    for f, v in zip(("ln_w", "ln_b", "conv_w", "conv_b", "se_w1", "se_w2"), tensors):
+        setattr(t, f, _p(v))
+    return t
+
+
+def conv_half_desc(B, C, T, E, kernel, pad, se_hidden, act, use_se, use_max, training, site, p, seed, step, step_dev=None):
+    return L.MmxConvHalfDesc(B, C, T, E, kernel[0], kernel[1], pad[0], pad[1], se_hidden, L.MMX_ACT[act], int(use_se),
+                             int(use_max), int(training), site, L.MmxDropout(float(p), int(seed), int(step), step_dev))
+
+
+class _ConvHalf(torch.autograd.Function):
+    """One half of ConvMixerBlock.forward (conv_mixer_model.py:279-284 / :287-292): y = x + SE(reg(act(conv(LN(x)))))."""
+
+    @staticmethod
+    def forward(ctx, x, meta, *params):
+        x = _chk(x, "x")
+        params = [None if q is None else _chk(q, "parameter") for q in params]
+        B, C, T, E = x.shape
+        desc = conv_half_desc(B, C, T, E, *meta)
+        y = torch.empty_like(x)
+        with torch.cuda.device_of(x):
+            _call("mmx_conv_half_fwd", C_.byref(desc), C_.byref(conv_half_table(params)), _p(x), _p(y), _stream())
+        ctx.save_for_backward(x, *[q for q in params if q is not None])
+        ctx.has = [q is not None for q in params]
+        ctx.meta = meta
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, *rest = ctx.saved_tensors
+        it = iter(rest)
+        params = [next(it) if h else None for h in ctx.has]
+        dy = _chk(dy, "grad")
+        B, C, T, E = x.shape
+        desc = conv_half_desc(B, C, T, E, *ctx.meta)
+        grads = _zeros_like_many(params)
+        dx = torch.empty_like(x)
+        with torch.cuda.device_of(x):
+            _call("mmx_conv_half_bwd", C_.byref(desc), C_.byref(conv_half_table(params)), C_.byref(conv_half_table(grads)),
+                  _p(x), _p(dy), _p(dx), _stream())
+        return (dx, None, *grads)
+
+
+def conv_half(x, meta, params):
+    """meta = (kernel, pad, se_hidden, act, use_se, use_max, training, site, p, seed, step)."""
+    return _ConvHalf.apply(x, meta, *params)
+
+
+class _SeTail(torch.autograd.Function):
+    """mode_conv='once': y = x + se(x), or 2x without SE (conv_mixer_model.py:259-263,287-292)."""
+
+    @staticmethod
+    def forward(ctx, x, meta, se_w1, se_w2):
+        x = _chk(x, "x")
+        se_hidden, use_se, use_max = meta
+        if use_se:
+            se_w1, se_w2 = _chk(se_w1, "se weight"), _chk(se_w2, "se weight")
+        B, C, T, E = x.shape
+        y = torch.empty_like(x)
+        with torch.cuda.device_of(x):
+            _call("mmx_se_tail_fwd", B, C, T, E, se_hidden, int(use_se), int(use_max), _p(se_w1), _p(se_w2), _p(x), _p(y), _stream())
+        if use_se:
+            ctx.save_for_backward(x, se_w1, se_w2)
+        else:
+            ctx.save_for_backward(x)
+        ctx.meta = meta
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        se_hidden, use_se, use_max = ctx.meta
+        x, *se = ctx.saved_tensors
+        dy = _chk(dy, "grad")
+        B, C, T, E = x.shape
+        g1 = g2 = None
+        if use_se:
+            g1, g2 = _zeros_like_many(se)
+        dx = torch.empty_like(x)
+        with torch.cuda.device_of(x):
+            _call("mmx_se_tail_bwd", B, C, T, E, se_hidden, int(use_se), int(use_max), _p(se[0]) if use_se else None,
+                  _p(se[1]) if use_se else None, _p(g1), _p(g2), _p(x), _p(dy), _p(dx), _stream())
+        return dx, None, g1, g2
+
+
+def se_tail(x, se_hidden, use_se, use_max, se_w1, se_w2):
+    return _SeTail.apply(x, (se_hidden, use_se, use_max), se_w1, se_w2)
+
+
+def encoder_table(tensors):
+    t = L.MmxEncoderParams()
+    for f, v in zip(("freq", "w", "b", "wc", "bc"), tensors):
+        setattr(t, f, _p(v))
+    return t
+
+
+class _PoseEncoder(torch.autograd.Function):
+    """PoseEncoder.forward (positional_encoder.py:79-97)."""
+
+    @staticmethod
+    def forward(ctx, x, n_harmonic, C, freq, w, b, wc, bc):
+        x, w, b, wc, bc = _chk(x, "x"), _chk(w, "weight"), _chk(b, "bias"), _chk(wc, "weight"), _chk(bc, "bias")
+        if n_harmonic > 0:
+            freq = _chk(freq, "frequencies")
+        B, T, D = x.shape
+        E = b.numel()
+        desc = L.MmxEncoderDesc(B, T, D, E, C, n_harmonic)
+        m = torch.empty(B * T, E, dtype=torch.float32, device=x.device)
+        y = torch.empty(B, C, T, E, dtype=torch.float32, device=x.device)
+        with torch.cuda.device_of(x):
+            _call("mmx_pose_encoder_fwd", C_.byref(desc), C_.byref(encoder_table([freq, w, b, wc, bc])), _p(x), _p(m), _p(y), _stream())
+        ctx.save_for_backward(x, m, w, b, wc, bc, *([freq] if n_harmonic > 0 else []))
+        ctx.dims = (B, T, D, E, C, n_harmonic)
+        ctx.need_dx = x.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, m, w, b, wc, bc, *fr = ctx.saved_tensors
+        freq = fr[0] if fr else None
+        dy = _chk(dy, "grad")
+        B, T, D, E, C, Hn = ctx.dims
+        desc = L.MmxEncoderDesc(B, T, D, E, C, Hn)
+        gw, gb, gwc, gbc = _zeros_like_many([w, b, wc, bc])
+        dm = torch.empty_like(m)
+        dx = torch.empty_like(x) if ctx.need_dx else None
+        with torch.cuda.device_of(x):
+            _call("mmx_pose_encoder_bwd", C_.byref(desc), C_.byref(encoder_table([freq, w, b, wc, bc])),
+                  C_.byref(encoder_table([None, gw, gb, gwc, gbc])), _p(x), _p(m), _p(dy), _p(dm), _p(dx), _stream())
+        return dx, None, None, None, gw, gb, gwc, gbc
+
+
+def pose_encoder(x, n_harmonic, C, freq, w, b, wc, bc):
+    return _PoseEncoder.apply(x, n_harmonic, C, freq, w, b, wc, bc)
+
+
+def conv_head_table(tensors):
+    t = L.MmxConvHeadParams()
+    for f, v in zip(("ln_w", "ln_b", "wt", "bt", "wp", "bp", "wf", "bf"), tensors):
+        setattr(t, f, _p(v))
+    return t
+
+
+class _ConvHead(torch.autograd.Function):
+    """LN -> conv_out -> project_channels -> GELU -> fc_out (conv_mixer_model.py:455-463)."""
+
+    @staticmethod
+    def forward(ctx, y, *params):
+        y = _chk(y, "y")
+        params = [_chk(q, "parameter") for q in params]
+        B, C, T, E = y.shape
+        To, D = params[3].numel(), params[7].numel()
+        desc = L.MmxConvHeadDesc(B, C, T, To, E, D)
+        out = torch.empty(B, To, D, dtype=torch.float32, device=y.device)
+        with torch.cuda.device_of(y):
+            _call("mmx_conv_head_fwd", C_.byref(desc), C_.byref(conv_head_table(params)), _p(y), _p(out), _stream())
+        ctx.save_for_backward(y, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, *params = ctx.saved_tensors
+        dout = _chk(dout, "grad")
+        B, C, T, E = y.shape
+        To, D = params[3].numel(), params[7].numel()
+        desc = L.MmxConvHeadDesc(B, C, T, To, E, D)
+        grads = _zeros_like_many(params)
+        dy = torch.empty_like(y)
+        with torch.cuda.device_of(y):
+            _call("mmx_conv_head_bwd", C_.byref(desc), C_.byref(conv_head_table(params)), C_.byref(conv_head_table(grads)),
+                  _p(y), _p(dout), _p(dy), _stream())
+        return (dy, *grads)
+
+
+def conv_head(y, ln_w, ln_b, wt, bt, wp, bp, wf, bf):
+    return _ConvHead.apply(y, ln_w, ln_b, wt, bt, wp, bp, wf, bf)

@@ -131,15 +131,97 @@ class _MlpMixerPlan:
         L.check(lib, lib.mmx_linear_bwd(self.B * T, D, H, _p(self.x), _p(self.conv_w), _p(cur), _p(self.conv_gw), _p(self.conv_gb), None, st), "mmx_linear_bwd")
 
 
+class _ConvMixerPlan:
+    """Pointer tables + static activations for one (ConvMixer, batch size)."""
+
+    def __init__(self, model, flat, B, dropout_step_dev):
+        from .conv_mixer_model import ConvMixer
+        assert isinstance(model, ConvMixer)
+        self.model, self.B = model, B
+        dev = flat.p.device
+        T, D, E, C = model.in_nTP, model.dimPosIn, model.dimPosEmb, model.conv_nChan
+        To, Dout = model.out_nTP, model.dimPosOut
+        enc = model.encoder
+        self.Hn = max(int(enc.n_harmonic_functions), 0)
+        self.x = torch.zeros(B, T, D, device=dev)
+        self.m = torch.empty(B * T, E, device=dev)
+        self.dm = torch.empty(B * T, E, device=dev)
+        self.step_dev = dropout_step_dev
+        self.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        ep = [enc.frequencies if self.Hn > 0 else None, enc.embed_mlp.weight, enc.embed_mlp.bias,
+              enc.channelUpscaling.weight, enc.channelUpscaling.bias]
+        self.enc_w = F_.encoder_table(ep)
+        self.enc_g = F_.encoder_table([None] + [flat.grad_of(q) for q in ep[1:]])
+        self.enc_desc = L.MmxEncoderDesc(B, T, D, E, C, self.Hn)
+        # ops in execution order: ("half", block, half, params table, grads table) | ("tail", block, se ptrs)
+        self.ops = []
+        for mb in model.Mixer_Block:
+            if mb.regularization == -1.0:
+                raise NotImplementedError("TrainStep: BatchNorm (regularization=-1) ConvMixerBlocks are not built yet")
+            for half in ((0, 1) if mb.mode_conv == "twice" else (0,)):
+                hp = mb.half_params(half)
+                self.ops.append(("half", mb, half, F_.conv_half_table(hp), F_.conv_half_table([flat.grad_of(q) for q in hp])))
+            if mb.mode_conv != "twice":
+                s1, s2 = mb.se_weights()
+                self.ops.append(("tail", mb, 1, (s1, s2), (flat.grad_of(s1), flat.grad_of(s2))))
+        self.acts = [torch.empty(B, C, T, E, device=dev) for _ in range(len(self.ops) + 1)]
+        self.pred = torch.empty(B, To, Dout, device=dev)
+        self.dpred = torch.empty_like(self.pred)
+        self.dact = [torch.empty(B, C, T, E, device=dev) for _ in range(2)]
+        hp = model.head_params()
+        self.head_w = F_.conv_head_table(hp)
+        self.head_g = F_.conv_head_table([flat.grad_of(q) for q in hp])
+        self.head_desc = L.MmxConvHeadDesc(B, C, T, To, E, Dout)
+        self.n_launches_fwd = 2 + len(self.ops)
+        self.n_launches_bwd = 1 + len(self.ops) + (2 if self.Hn == 0 else 3)
+
+    def _desc(self, mb, half, training):
+        m = mb.half_meta(half, self.seed, 0)
+        md = self.model
+        return F_.conv_half_desc(self.B, md.conv_nChan, md.in_nTP, md.dimPosEmb, *m[:6], training, *m[7:],
+                                 step_dev=_p(self.step_dev) if training else None)
+
+    def _tail(self, lib, fn, mb, st, *ptrs):
+        md = self.model
+        return getattr(lib, fn)(self.B, md.conv_nChan, md.in_nTP, md.dimPosEmb, md.in_nTP // mb.r_se if mb.use_se else 0,
+                                int(mb.use_se), int(mb.use_max_pooling), *ptrs, st)
+
+    def forward(self, lib, st, training):
+        L.check(lib, lib.mmx_pose_encoder_fwd(C.byref(self.enc_desc), C.byref(self.enc_w), _p(self.x), _p(self.m), _p(self.acts[0]), st),
+                "mmx_pose_encoder_fwd")
+        for i, (kind, mb, half, tw, _) in enumerate(self.ops):
+            if kind == "half":
+                d = self._desc(mb, half, training)
+                L.check(lib, lib.mmx_conv_half_fwd(C.byref(d), C.byref(tw), _p(self.acts[i]), _p(self.acts[i + 1]), st), "mmx_conv_half_fwd")
+            else:
+                L.check(lib, self._tail(lib, "mmx_se_tail_fwd", mb, st, _p(tw[0]), _p(tw[1]), _p(self.acts[i]), _p(self.acts[i + 1])), "mmx_se_tail_fwd")
+        L.check(lib, lib.mmx_conv_head_fwd(C.byref(self.head_desc), C.byref(self.head_w), _p(self.acts[-1]), _p(self.pred), st), "mmx_conv_head_fwd")
+        return self.pred
+
+    def backward(self, lib, st):
+        cur = self.dact[0]
+        L.check(lib, lib.mmx_conv_head_bwd(C.byref(self.head_desc), C.byref(self.head_w), C.byref(self.head_g),
+                                           _p(self.acts[-1]), _p(self.dpred), _p(cur), st), "mmx_conv_head_bwd")
+        for i in reversed(range(len(self.ops))):
+            kind, mb, half, tw, tg = self.ops[i]
+            nxt = self.dact[1] if cur is self.dact[0] else self.dact[0]
+            if kind == "half":
+                d = self._desc(mb, half, True)
+                L.check(lib, lib.mmx_conv_half_bwd(C.byref(d), C.byref(tw), C.byref(tg), _p(self.acts[i]), _p(cur), _p(nxt), st), "mmx_conv_half_bwd")
+            else:
+                L.check(lib, self._tail(lib, "mmx_se_tail_bwd", mb, st, _p(tw[0]), _p(tw[1]), _p(tg[0]), _p(tg[1]),
+                                        _p(self.acts[i]), _p(cur), _p(nxt)), "mmx_se_tail_bwd")
+            cur = nxt
+        L.check(lib, lib.mmx_pose_encoder_bwd(C.byref(self.enc_desc), C.byref(self.enc_w), C.byref(self.enc_g), _p(self.x), _p(self.m),
+                                              _p(cur), _p(self.dm), None, st), "mmx_pose_encoder_bwd")
+
+
 def _make_plan(model, flat, B, step_dev):
     from .mlp_mixer import MlpMixer
+    from .conv_mixer_model import ConvMixer
     if isinstance(model, MlpMixer):
         return _MlpMixerPlan(model, flat, B, step_dev)
-    try:
-        from .conv_mixer_model import ConvMixer, _ConvMixerPlan
-    except ImportError:
-        ConvMixer = None
-    if ConvMixer is not None and isinstance(model, ConvMixer):
+    if isinstance(model, ConvMixer):
         return _ConvMixerPlan(model, flat, B, step_dev)
     raise TypeError("TrainStep supports motionmixerconv_b200 MlpMixer / ConvMixer, got %s" % type(model).__name__)
 
@@ -167,7 +249,7 @@ class TrainStep:
         self.device = dev
         # optimiser clock and hyper-parameters live on the device (mmx_adam_advance): nothing is
         # written from the host per step, so the step is replayable from a CUDA graph
-        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, 1.0, 1.0, 1.0 / self.world],
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, 1.0, 1.0, 1.0 / self.world, 1 - betas[0], 1 - betas[1]],
                                   dtype=torch.float32, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -293,7 +375,8 @@ class FusedAdam(torch.optim.Optimizer):
                 v.copy_(p.data)
                 p.data = v
         st = dict(ps=ps, offs=offs, p=flat, g=torch.zeros_like(flat), m=torch.zeros_like(flat), v=torch.zeros_like(flat),
-                  hyper=torch.tensor([group["lr"], group["betas"][0], group["betas"][1], group["eps"], group["weight_decay"], 1.0, 1.0, 1.0],
+                  hyper=torch.tensor([group["lr"], group["betas"][0], group["betas"][1], group["eps"], group["weight_decay"], 1.0, 1.0, 1.0,
+                                      1 - group["betas"][0], 1 - group["betas"][1]],
                                      dtype=torch.float32, device=dev),
                   step=torch.zeros(1, dtype=torch.int32, device=dev), lr=group["lr"])
         self._flat[gi] = st

@@ -153,5 +153,139 @@ def mpjpe(pred, gt, gscale=1.0):
 
 
 def adam_step(p, g, m, v, step, lr=1e-3, wd=1e-5, b1=0.9, b2=0.999, eps=1e-8, gscale=1.0):
-    hp = np.array([lr, b1, b2, eps, wd, 1 - b1 ** step, np.sqrt(1 - b2 ** step), gscale], np.float32)
+    hp = np.array([lr, b1, b2, eps, wd, 1 - b1 ** step, np.sqrt(1 - b2 ** step), gscale, 1 - b1, 1 - b2], np.float32)
     call("mmx_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.size, ptr(hp), None)
+
+
+# ---------------------------------------------------------------------------------------------
+# ConvMixer assembled from the C-ABI ops (mirrors motionmixerconv_b200/conv_mixer_model.py, numpy arrays)
+# ---------------------------------------------------------------------------------------------
+def conv_geometry(cfg):
+    """-> (k1, pad1, k2, pad2) with pads as (top, left); k2 / pad2 None for mode_conv='once'."""
+    k1 = tuple(cfg.get("conv1_kernel_shape", (1, 3)))
+    p1 = cfg.get("conv1_padding")
+    pad1 = ((k1[0] - 1) // 2, (k1[1] - 1) // 2) if p1 is None else tuple(p1)
+    if cfg.get("mode_conv", "twice") != "twice":
+        return k1, pad1, None, None
+    k2 = cfg.get("conv2_kernel_shape")
+    if k2 is None:
+        k2 = (min(k1[1], cfg["in_nTP"]), min(k1[0], cfg["dimPosEmb"]))
+    k2 = tuple(k2)
+    p2 = cfg.get("conv2_padding")
+    pad2 = ((k2[0] - 1) // 2, (k2[1] - 1) // 2) if p2 is None else tuple(p2)
+    return k1, pad1, k2, pad2
+
+
+class EmuConvMixer:
+    def __init__(self, cfg, params, training=True, dropout=None):
+        self.cfg = dict(cfg)
+        self.p = {k: f32(v) for k, v in params.items() if np.asarray(v).dtype.kind == "f"}
+        self.training = training
+        self.dropout = dropout or dropout_struct()
+        c = self.cfg
+        self.C = c.get("conv_nChan", 1)
+        self.T, self.To, self.E = c["in_nTP"], c["out_nTP"], c["dimPosEmb"]
+        self.D, self.Dout = c["dimPosIn"], c["dimPosOut"]
+        self.Hn = max(c.get("encoder_n_harmonic_functions", 64), 0)
+        self.use_se = bool(c.get("use_se", False))
+        self.use_max = bool(c.get("use_max_pooling", False))
+        self.rr = self.T // c.get("r_se", 4)
+        self.act = L.MMX_ACT[c.get("activation", "gelu")]
+        self.twice = c.get("mode_conv", "twice") == "twice"
+        self.k1, self.pad1, self.k2, self.pad2 = conv_geometry(c)
+
+    def _half_tables(self, i, half, src):
+        t = L.MmxConvHalfParams()
+        pre = "Mixer_Block.%d." % i
+        ln, cv = ("LN1", "conv1") if half == 0 else ("LN2", "conv2")
+        t.ln_w, t.ln_b = ptr(src[pre + ln + ".weight"]), ptr(src[pre + ln + ".bias"])
+        t.conv_w, t.conv_b = ptr(src[pre + cv + ".conv.weight"]), ptr(src[pre + cv + ".conv.bias"])
+        if self.use_se:
+            t.se_w1, t.se_w2 = ptr(src[pre + "se.excitationBlock.0.weight"]), ptr(src[pre + "se.excitationBlock.2.weight"])
+        return t
+
+    def _half_desc(self, i, half, B):
+        k, pad = (self.k1, self.pad1) if half == 0 else (self.k2, self.pad2)
+        return L.MmxConvHalfDesc(B, self.C, self.T, self.E, k[0], k[1], pad[0], pad[1], self.rr, self.act, int(self.use_se),
+                                 int(self.use_max), int(self.training), 2 * i + half, self.dropout)
+
+    def _enc(self, src):
+        t = L.MmxEncoderParams()
+        t.freq = ptr(self.p["encoder.frequencies"]) if self.Hn > 0 else None
+        t.w, t.b = ptr(src["encoder.embed_mlp.weight"]), ptr(src["encoder.embed_mlp.bias"])
+        t.wc, t.bc = ptr(src["encoder.channelUpscaling.weight"]), ptr(src["encoder.channelUpscaling.bias"])
+        return t
+
+    def _head(self, src):
+        t = L.MmxConvHeadParams()
+        t.ln_w, t.ln_b = ptr(src["LN.weight"]), ptr(src["LN.bias"])
+        t.wt, t.bt = ptr(src["conv_out.weight"]), ptr(src["conv_out.bias"])
+        t.wp, t.bp = ptr(src["project_channels.weight"]), ptr(src["project_channels.bias"])
+        t.wf, t.bf = ptr(src["fc_out.weight"]), ptr(src["fc_out.bias"])
+        return t
+
+    def forward(self, x):
+        x = f32(x)
+        B = x.shape[0]
+        C, T, E = self.C, self.T, self.E
+        self.x = x
+        self.m = np.empty((B * T, E), np.float32)
+        y = np.empty((B, C, T, E), np.float32)
+        ed = L.MmxEncoderDesc(B, T, self.D, E, C, self.Hn)
+        call("mmx_pose_encoder_fwd", _byref(ed), _byref(self._enc(self.p)), ptr(x), ptr(self.m), ptr(y), None)
+        self.acts = [y]           # inputs of every half / tail, in execution order
+        self.ops = []
+        for i in range(self.cfg["num_blocks"]):
+            for half in ((0, 1) if self.twice else (0,)):
+                out = np.empty_like(y)
+                call("mmx_conv_half_fwd", _byref(self._half_desc(i, half, B)), _byref(self._half_tables(i, half, self.p)),
+                     ptr(self.acts[-1]), ptr(out), None)
+                self.acts.append(out)
+                self.ops.append(("half", i, half))
+            if not self.twice:
+                out = np.empty_like(y)
+                pre = "Mixer_Block.%d." % i
+                s1 = ptr(self.p[pre + "se.excitationBlock.0.weight"]) if self.use_se else None
+                s2 = ptr(self.p[pre + "se.excitationBlock.2.weight"]) if self.use_se else None
+                call("mmx_se_tail_fwd", B, C, T, E, self.rr, int(self.use_se), int(self.use_max), s1, s2, ptr(self.acts[-1]), ptr(out), None)
+                self.acts.append(out)
+                self.ops.append(("tail", i, 1))
+        pred = np.empty((B, self.To, self.Dout), np.float32)
+        hd = L.MmxConvHeadDesc(B, C, T, self.To, E, self.Dout)
+        call("mmx_conv_head_fwd", _byref(hd), _byref(self._head(self.p)), ptr(self.acts[-1]), ptr(pred), None)
+        return pred
+
+    def backward(self, dout, need_dx=True):
+        dout = f32(dout)
+        B = self.x.shape[0]
+        C, T, E = self.C, self.T, self.E
+        g = {k: np.zeros_like(v) for k, v in self.p.items()}
+        d_act = np.empty((B, C, T, E), np.float32)
+        hd = L.MmxConvHeadDesc(B, C, T, self.To, E, self.Dout)
+        call("mmx_conv_head_bwd", _byref(hd), _byref(self._head(self.p)), _byref(self._head(g)), ptr(self.acts[-1]), ptr(dout), ptr(d_act), None)
+        for n in reversed(range(len(self.ops))):
+            kind, i, half = self.ops[n]
+            dx = np.empty_like(d_act)
+            if kind == "half":
+                call("mmx_conv_half_bwd", _byref(self._half_desc(i, half, B)), _byref(self._half_tables(i, half, self.p)),
+                     _byref(self._half_tables(i, half, g)), ptr(self.acts[n]), ptr(d_act), ptr(dx), None)
+            else:
+                pre = "Mixer_Block.%d." % i
+                k1, k2 = pre + "se.excitationBlock.0.weight", pre + "se.excitationBlock.2.weight"
+                s = [ptr(self.p[k1]), ptr(self.p[k2]), ptr(g[k1]), ptr(g[k2])] if self.use_se else [None] * 4
+                call("mmx_se_tail_bwd", B, C, T, E, self.rr, int(self.use_se), int(self.use_max), *s, ptr(self.acts[n]), ptr(d_act), ptr(dx), None)
+            d_act = dx
+        dm = np.empty((B * T, E), np.float32)
+        dxin = np.empty_like(self.x) if need_dx else None
+        ed = L.MmxEncoderDesc(B, T, self.D, E, C, self.Hn)
+        call("mmx_pose_encoder_bwd", _byref(ed), _byref(self._enc(self.p)), _byref(self._enc(g)), ptr(self.x), ptr(self.m),
+             ptr(d_act), ptr(dm), ptr(dxin), None)
+        for k in list(g):
+            if ".se2." in k:          # alias of .se. in the reference state_dict
+                g.pop(k)
+        g.pop("encoder.frequencies", None)
+        return g, dxin
+
+
+def _byref(s):
+    return C.byref(s)

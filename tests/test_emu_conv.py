@@ -1,0 +1,69 @@
+"""CPU: the ConvMixer kernel SOURCE (csrc/mmx_conv*.cuh) run phase by phase in the host emulator
+(tests/emu/harness.py — test infrastructure) against the golden fixtures generated from the reference.
+
+This is what keeps indexing / math of the CUDA kernels checkable in a container without a GPU; the GPU
+parity tests proper are tests/test_gpu_conv.py (-m gpu).
+"""
+import numpy as np
+import pytest
+
+from oracle import mixer_np as O
+from tests.emu import harness as H
+from tests.golden_util import Golden, check_close, golden_cases, grad_scale
+
+TOL = 1e-5
+CONV_CASES = [c for c in golden_cases("conv") if not c.endswith("_bn")]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_emulated_kernels_match_golden(case):
+    g = Golden(case)
+    n = min(g.x.shape[0], 6)                       # the emulator is slow: a few sequences are enough for indexing
+    x, gt = g.x[:n], g.gt[:n]
+    o64 = O.ConvMixerOracle(g.cfg, g.params, dtype=np.float64)
+    p64 = o64.forward(x)
+    l64, dp64 = O.mpjpe(p64, gt.astype(np.float64))
+    g64, dx64 = o64.backward(dp64)
+    o32 = O.ConvMixerOracle(g.cfg, g.params, dtype=np.float32)
+    p32 = o32.forward(x)
+    l32, dp32 = O.mpjpe(p32, gt)
+    g32, dx32 = o32.backward(dp32)
+
+    m = H.EmuConvMixer(g.cfg, g.params, training=True)
+    pred = m.forward(x)
+    check_close("pred", pred, p32, p64, rtol=TOL)
+    loss, dpred = H.mpjpe(pred, gt)
+    assert abs(loss - float(l64)) <= TOL * abs(float(l64))
+    grads, dx = m.backward(dpred)
+    floor = 1e-6 * grad_scale(g32)
+    for k in O.trainable_keys(g.params):
+        check_close("grad " + k, grads[k], g32[k], g64[k], rtol=TOL, atol=floor)
+    check_close("dx", dx, dx32, dx64, rtol=TOL, atol=1e-6 * float(np.abs(dx32).max()))
+
+
+@pytest.mark.parametrize("case,B,S,xg", [("conv_k1", 7, 2, 0), ("conv_k3", 3, 1, 1), ("conv_once_se", 5, 2, 1), ("conv_evenk", 5, 3, 0)])
+def test_emulated_multi_tile_and_streamed_inputs(case, B, S, xg, monkeypatch):
+    """Forced small tiles: several tiles per CTA with a ragged last one (the persistent loops, the accumulators
+    that live across tiles) — once with the backward's X / dY tiles in shared memory, once streamed from global."""
+    from tests.synthetic import synthetic_pose_windows
+    g = Golden(case)
+    c = g.cfg
+    x, gt = synthetic_pose_windows(B, c["in_nTP"], c["out_nTP"], c["dimPosIn"], scale="amass", seed=3)
+    o32 = O.ConvMixerOracle(c, g.params, dtype=np.float32)
+    o64 = O.ConvMixerOracle(c, g.params, dtype=np.float64)
+    p32, p64 = o32.forward(x), o64.forward(x)
+    _, dp32 = O.mpjpe(p32, gt)
+    _, dp64 = O.mpjpe(p64, gt.astype(np.float64))
+    (g32, dx32), (g64, dx64) = o32.backward(dp32), o64.backward(dp64)
+    for name in ("MMX_CONV_S_FWD", "MMX_CONV_S_BWD", "MMX_CHEAD_S_FWD", "MMX_CHEAD_S_BWD"):
+        monkeypatch.setenv(name, str(S))
+    monkeypatch.setenv("MMX_CONV_X_GLOBAL", str(xg))
+    m = H.EmuConvMixer(c, g.params, training=True)
+    pred = m.forward(x)
+    check_close("pred", pred, p32, p64, rtol=TOL)
+    _, dpred = H.mpjpe(pred, gt)
+    grads, dx = m.backward(dpred)
+    floor = 1e-6 * grad_scale(g32)
+    for k in O.trainable_keys(g.params):
+        check_close("grad " + k, grads[k], g32[k], g64[k], rtol=TOL, atol=floor)
+    check_close("dx", dx, dx32, dx64, rtol=TOL, atol=1e-6 * float(np.abs(dx32).max()))
