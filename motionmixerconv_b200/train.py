@@ -24,6 +24,7 @@ import torch.distributed as dist
 
 from . import _lib as L
 from . import functional as F_
+from . import parallel as P_
 from .functional import _p
 
 
@@ -43,11 +44,7 @@ class FlatBuffers:
         if dev.type != "cuda":
             raise RuntimeError("TrainStep needs the model on a CUDA device (model.to('cuda') first)")
         self.params = params
-        self.offsets = []
-        o = 0
-        for p in params:
-            self.offsets.append(o)
-            o += (p.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
+        self.offsets, o = P_.flat_offsets([p.numel() for p in params])   # every view 16-byte aligned
         self.numel = o
         self.p = torch.zeros(o, dtype=torch.float32, device=dev)
         self.g = torch.zeros_like(self.p)
@@ -305,14 +302,14 @@ class TrainStep:
         if not self.use_graph:
             self._fwd_bwd()
             if self.world > 1:
-                dist.all_reduce(self.flat.g, group=self.pg)
+                P_.allreduce_bucket(self.flat.g, self.pg)
             self._adam()
         else:
             if self.graph_a is None:
                 self._capture()
             self.graph_a.replay()
             if self.world > 1:
-                dist.all_reduce(self.flat.g, group=self.pg)
+                P_.allreduce_bucket(self.flat.g, self.pg)
             self.graph_b.replay()
         n_joints = pl.pred.numel() // 3
         return (self.loss_sum * (float(self.loss_scale) / n_joints)).reshape(())
