@@ -10,15 +10,17 @@ extern "C" int mmx_mlp_block_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockPara
                                  const float* x, const float* dy, float* dx, void* stream) {
     if (!x || !dy || !dx) return fail(MMX_E_INVALID, "mmx_mlp_block_bwd: null tensor");
     MlpBlockBwdArgs a;
-    size_t smem; int grid;
-    int rc = plan_mlp_block(d, true, &a.d, &smem, &grid);
+    size_t smem; int grid, nwarp = 0;
+    if (!d) return fail(MMX_E_INVALID, "null descriptor");
+    const bool warp_variant = mlp_warp_variant_ok(d);
+    int rc = warp_variant ? plan_mlp_block_warp(d, true, &a.d, &smem, &grid, &nwarp) : plan_mlp_block(d, true, &a.d, &smem, &grid);
     if (rc) return rc;
     if ((rc = check_block_params(w, d->use_se, "mmx_mlp_block_bwd"))) return rc;
     if ((rc = check_block_params(grads, d->use_se, "mmx_mlp_block_bwd(grads)"))) return rc;
     a.dr = make_dropout(d->dropout, d->training);
     a.w = to_w(w); a.g = to_w(grads); a.x = x; a.dy = dy; a.dx = dx;
     const int tiles = imax(((d->ch + 3) / 4) * ((d->H + 3) / 4), 1);
-    const int wt1 = tiles <= kThreads;
+    const int wt1 = warp_variant ? -nwarp : (tiles <= kThreads);
     return d->act == MMX_ACT_GELU ? mmx_mlp_bwd_launch_gelu(a, wt1, grid, smem, stream)
                                   : mmx_mlp_bwd_launch_mish(a, wt1, grid, smem, stream);
 }

@@ -7,6 +7,9 @@ namespace mmx_tu_mlp_fwd {
 template <int ACT, int TC, int TOKC>
 struct MlpFwdBody { static MMX_D void run(Exec& ex, const MlpBlockFwdArgs& a) { mlp_block_fwd_body<ACT, TC, TOKC>(ex, a); } };
 
+template <int ACT, int TC, int TOKC>
+struct MlpFwdWarpBody { static MMX_D void run(Exec& ex, const MlpBlockFwdArgs& a) { mlp_block_fwd_warp_body<ACT, TC, TOKC>(ex, a); } };
+
 template <int ACT>
 int dispatch_mlp_fwd(const MlpBlockFwdArgs& a, int grid, size_t smem, void* stream) {
     if (a.d.T == 10 && a.d.tok == 20) return launch<MlpFwdBody<ACT, 10, 20>>(a, grid, kThreads, smem, stream, 1);
@@ -18,11 +21,22 @@ using namespace mmx_tu_mlp_fwd;
 extern "C" int mmx_mlp_block_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* y, void* stream) {
     if (!x || !y) return fail(MMX_E_INVALID, "mmx_mlp_block_fwd: null tensor");
     MlpBlockFwdArgs a;
-    size_t smem; int grid;
-    int rc = plan_mlp_block(d, false, &a.d, &smem, &grid);
+    size_t smem; int grid, nwarp = 0;
+    if (!d) return fail(MMX_E_INVALID, "null descriptor");
+    const bool warp_variant = mlp_warp_variant_ok(d);
+    int rc = warp_variant ? plan_mlp_block_warp(d, false, &a.d, &smem, &grid, &nwarp) : plan_mlp_block(d, false, &a.d, &smem, &grid);
     if (rc) return rc;
     if ((rc = check_block_params(w, d->use_se, "mmx_mlp_block_fwd"))) return rc;
     a.dr = make_dropout(d->dropout, d->training);
     a.w = to_w(w); a.x = x; a.y = y;
+    if (warp_variant) {
+        const int thr = nwarp * 32;
+        const int occ = env_int("MMX_MLP_FWD_OCC", 1);   // 2: the 128-register build, two CTAs per SM
+        if (occ >= 2)
+            return d->act == MMX_ACT_GELU ? launch<MlpFwdWarpBody<ACT_GELU, 10, 20>, MlpBlockFwdArgs, 2>(a, grid, thr, smem, stream, 2)
+                                          : launch<MlpFwdWarpBody<ACT_MISH, 10, 20>, MlpBlockFwdArgs, 2>(a, grid, thr, smem, stream, 2);
+        return d->act == MMX_ACT_GELU ? launch<MlpFwdWarpBody<ACT_GELU, 10, 20>>(a, grid, thr, smem, stream, 1)
+                                      : launch<MlpFwdWarpBody<ACT_MISH, 10, 20>>(a, grid, thr, smem, stream, 1);
+    }
     return d->act == MMX_ACT_GELU ? dispatch_mlp_fwd<ACT_GELU>(a, grid, smem, stream) : dispatch_mlp_fwd<ACT_MISH>(a, grid, smem, stream);
 }

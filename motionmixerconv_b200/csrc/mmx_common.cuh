@@ -22,12 +22,14 @@
 #define MMX_HD inline
 #define MMX_D inline
 #define MMX_UNROLL
+#define MMX_NOUNROLL
 #define MMX_NOINLINE
 #else
 #include <cuda_runtime.h>
 #define MMX_HD __host__ __device__ __forceinline__
 #define MMX_D __device__ __forceinline__
 #define MMX_UNROLL _Pragma("unroll")
+#define MMX_NOUNROLL _Pragma("unroll 1")
 #define MMX_NOINLINE __noinline__
 #endif
 
@@ -64,6 +66,32 @@ MMX_D void smem_add(float* p, float v) {
 #endif
 }
 
+// CTA-scope spin lock in shared memory taken by one WARP: lane 0 acquires, the warp's other lanes wait at the
+// __syncwarp.  Protects short plain read-modify-write sections on accumulators shared by the CTA's warps (shared
+// memory has no native fp32 atomic add: atomicAdd(float) on shared compiles to a CAS loop per element).
+MMX_D void warp_lock(unsigned int* l, int lane) {
+#if defined(MMX_HOST_EMU)
+    (void)l; (void)lane;
+#else
+    if (lane == 0) {
+        while (atomicCAS(l, 0u, 1u) != 0u) { __nanosleep(32); }
+        __threadfence_block();
+    }
+    __syncwarp();
+#endif
+}
+MMX_D void warp_unlock(unsigned int* l, int lane) {
+#if defined(MMX_HOST_EMU)
+    (void)l; (void)lane;
+#else
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        atomicExch(l, 0u);
+    }
+#endif
+}
+
 MMX_HD int round_up(int x, int m) { return (x + m - 1) / m * m; }
 MMX_HD int imin(int a, int b) { return a < b ? a : b; }
 MMX_HD int imax(int a, int b) { return a > b ? a : b; }
@@ -84,6 +112,16 @@ MMX_HD int pitch_of(int w) {
 // ------------------------------------------------------------------------------------------
 enum { ACT_GELU = 0, ACT_MISH = 1 };
 
+// exp / divide of the activations: MUFU-based intrinsics on the GPU (<= 2 ulp + 2^-21 relative: two orders of
+// magnitude inside the 1e-5 parity bar; checked by the GPU parity tests), libm in the emulator
+#if defined(MMX_HOST_EMU)
+MMX_D float fast_exp(float x) { return expf(x); }
+MMX_D float fast_div(float a, float b) { return a / b; }
+#else
+MMX_D float fast_exp(float x) { return __expf(x); }
+MMX_D float fast_div(float a, float b) { return __fdividef(a, b); }
+#endif
+
 template <int ACT>
 MMX_D float act_fwd(float u) {
     if (ACT == ACT_GELU) {
@@ -91,9 +129,9 @@ MMX_D float act_fwd(float u) {
     } else {
         // u * tanh(softplus(u)); tanh(log(1+e)) = n/(n+2) with n = e*(e+2); softplus threshold 20
         if (u > 20.0f) return u;
-        float e = expf(u);
+        float e = fast_exp(u);
         float n = e * (e + 2.0f);
-        return u * (n / (n + 2.0f));
+        return u * fast_div(n, n + 2.0f);
     }
 }
 
@@ -103,21 +141,21 @@ MMX_D float act_fwd_grad(float u, float* a) {
     if (ACT == ACT_GELU) {
         float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
         *a = u * cdf;
-        return cdf + u * expf(-0.5f * u * u) * 0.39894228040143268f;
+        return cdf + u * fast_exp(-0.5f * u * u) * 0.39894228040143268f;
     } else {
         if (u > 20.0f) { *a = u; return 1.0f; }
-        float e = expf(u);
+        float e = fast_exp(u);
         float n = e * (e + 2.0f);
-        float inv = 1.0f / (n + 2.0f);
+        float inv = fast_div(1.0f, n + 2.0f);
         float t = n * inv;                        // tanh(softplus(u))
         float omt2 = 4.0f * (n + 1.0f) * inv * inv;  // 1 - t^2
-        float sig = e / (1.0f + e);
+        float sig = fast_div(e, 1.0f + e);
         *a = u * t;
         return t + u * omt2 * sig;
     }
 }
 
-MMX_D float sigmoidf_(float q) { return 1.0f / (1.0f + expf(-q)); }
+MMX_D float sigmoidf_(float q) { return fast_div(1.0f, 1.0f + fast_exp(-q)); }
 
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10 (dropout masks).  Counter = (c0,c1,c2,c3), key = (k0,k1).
@@ -169,16 +207,68 @@ float dropout_scale(const Dropout& d, uint32_t site, uint64_t elem) {
     return v >= d.thresh ? d.scale : 0.0f;
 }
 
+// Two quads per Philox call (16 random bits per element): `pair` numbers consecutive row pairs of a [rows][W] site,
+// ks0 / ks1 are the keep-scales of quad `q` of the pair's first / second row.  Philox4x32-7 (Crush-resistant per
+// Salmon et al., SC'11): the masks only need to be uncorrelated, not cryptographic.
+#if defined(MMX_HOST_EMU)
+inline
+#else
+static __device__ __noinline__
+#endif
+void dropout_rowpair(const Dropout& d, uint32_t site, uint64_t pair, int q, int W4, float (&ks0)[4], float (&ks1)[4]) {
+    const uint64_t ctr = pair * (uint64_t)W4 + (uint64_t)q;
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = site ^ 0x5bd1e995u, c3 = d.step, k0 = d.seed_lo, k1 = d.seed_hi;
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    MMX_UNROLL
+    for (int i = 0; i < 7; ++i) {
+        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3; k0 += W0; k1 += W1;
+    }
+    const uint32_t th = d.thresh >> 16;   // keep iff the 16-bit field >= th
+    ks0[0] = (c0 & 0xffffu) >= th ? d.scale : 0.0f; ks0[1] = (c0 >> 16) >= th ? d.scale : 0.0f;
+    ks0[2] = (c1 & 0xffffu) >= th ? d.scale : 0.0f; ks0[3] = (c1 >> 16) >= th ? d.scale : 0.0f;
+    ks1[0] = (c2 & 0xffffu) >= th ? d.scale : 0.0f; ks1[1] = (c2 >> 16) >= th ? d.scale : 0.0f;
+    ks1[2] = (c3 & 0xffffu) >= th ? d.scale : 0.0f; ks1[3] = (c3 >> 16) >= th ? d.scale : 0.0f;
+}
+
+// Quad-granular masks: a dropout site is a [rows][W] tensor with W4 = ceil(W/4) quads per row; quad number
+// row*W4 + w/4 is one Philox counter and yields the keep-scales of its 4 elements.
+#if defined(MMX_HOST_EMU)
+inline
+#else
+static __device__ __noinline__
+#endif
+void dropout_quad(const Dropout& d, uint32_t site, uint64_t quad, float (&s)[4]) {
+    u4 r = philox4x32_10((uint32_t)quad, (uint32_t)(quad >> 32), site, d.step, d.seed_lo, d.seed_hi);
+    s[0] = r.x >= d.thresh ? d.scale : 0.0f; s[1] = r.y >= d.thresh ? d.scale : 0.0f;
+    s[2] = r.z >= d.thresh ? d.scale : 0.0f; s[3] = r.w >= d.thresh ? d.scale : 0.0f;
+}
+
 // ------------------------------------------------------------------------------------------
 // executors
 // ------------------------------------------------------------------------------------------
 #if defined(MMX_HOST_EMU)
+// warp-level executor: sub-phases of ONE warp, separated by __syncwarp() on the GPU (lanes may exchange data
+// through shared memory between sub-phases); the emulator runs each sub-phase as a loop over the 32 lanes
+struct WarpExec {
+    int warp, nwarp;
+    template <class F>
+    void phase(F&& f) {
+        for (int l = 0; l < 32; ++l) f(l);
+    }
+};
 struct Exec {
     int nthr, bid, nblk;
     float* smem;
     template <class F>
     void phase(F&& f) {
         for (int t = 0; t < nthr; ++t) f(t);
+    }
+    // run body(WarpExec&) once per warp of the CTA; warps do not communicate inside (no CTA barrier implied)
+    template <class F>
+    void warps(F&& body) {
+        for (int w = 0; w < nthr / 32; ++w) { WarpExec wx{w, nthr / 32}; body(wx); }
     }
 };
 template <class T>
@@ -188,6 +278,14 @@ struct PerThread {
     T& operator[](int tid) { return v[tid]; }
 };
 #else
+struct WarpExec {
+    int warp, nwarp;
+    template <class F>
+    __device__ __forceinline__ void phase(F&& f) {
+        f((int)(threadIdx.x & 31));
+        __syncwarp();
+    }
+};
 struct Exec {
     int nthr, bid, nblk;
     float* smem;
@@ -195,6 +293,11 @@ struct Exec {
     __device__ __forceinline__ void phase(F&& f) {
         f((int)threadIdx.x);
         __syncthreads();
+    }
+    template <class F>
+    __device__ __forceinline__ void warps(F&& body) {
+        WarpExec wx{(int)(threadIdx.x >> 5), (int)(blockDim.x >> 5)};
+        body(wx);
     }
 };
 template <class T>

@@ -91,15 +91,6 @@ MMX_HD ConvSmem conv_smem(const ConvDims& d, bool bwd) {
 }
 
 // ------------------------------------------------------------------------------------------
-// dropout: keep-scales of one aligned quad of a row ([rows][E] tensor, E4 = ceil(E/4) quads per row)
-// ------------------------------------------------------------------------------------------
-MMX_D void dropout_quad(const Dropout& d, uint32_t site, uint64_t quad, float (&s)[4]) {
-    u4 r = philox4x32_10((uint32_t)quad, (uint32_t)(quad >> 32), site, d.step, d.seed_lo, d.seed_hi);
-    s[0] = r.x >= d.thresh ? d.scale : 0.0f; s[1] = r.y >= d.thresh ? d.scale : 0.0f;
-    s[2] = r.z >= d.thresh ? d.scale : 0.0f; s[3] = r.w >= d.thresh ? d.scale : 0.0f;
-}
-
-// ------------------------------------------------------------------------------------------
 // row reductions with kParts threads per row.  Part p handles quads p, p+kParts, ... of the row.
 // ------------------------------------------------------------------------------------------
 MMX_D float row_part_sum(const float* row, int W, int p) {

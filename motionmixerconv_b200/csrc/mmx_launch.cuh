@@ -28,7 +28,7 @@ static inline int env_int(const char* name, int dflt) {
 struct DevInfo { int sms = 4; int max_smem = 227 * 1024; };
 static inline DevInfo dev_info() { return DevInfo(); }
 
-template <class Body, class Args>
+template <class Body, class Args, int OCC = 1>
 static int launch(const Args& a, int grid, int block, size_t smem_bytes, void*, int /*min_blocks*/) {
     std::vector<float> buf(smem_bytes / 4 + 8);
     float* sm = buf.data();
@@ -64,17 +64,27 @@ static __global__ void __launch_bounds__(256) mmx_kernel(const Args a) {
     Body::run(ex, a);
 }
 
+// same kernel compiled for two resident CTAs per SM (<= 128 registers per thread)
 template <class Body, class Args>
+static __global__ void __launch_bounds__(256, 2) mmx_kernel_occ2(const Args a) {
+    extern __shared__ float4 mmx_smem_raw[];
+    Exec ex{(int)blockDim.x, (int)blockIdx.x, (int)gridDim.x, reinterpret_cast<float*>(mmx_smem_raw)};
+    Body::run(ex, a);
+}
+
+template <class Body, class Args, int OCC = 1>
 static int launch(const Args& a, int grid, int block, size_t smem_bytes, void* stream, int /*min_blocks*/) {
-    auto kern = mmx_kernel<Body, Args>;
-    static size_t configured[64] = {};
+    constexpr int min_blocks = OCC;
+    auto kern = OCC >= 2 ? mmx_kernel_occ2<Body, Args> : mmx_kernel<Body, Args>;
+    static size_t configured[2][64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
-    if (smem_bytes > 48 * 1024 && configured[dev] < smem_bytes) {
+    size_t& conf = configured[min_blocks >= 2 ? 1 : 0][dev];
+    if (smem_bytes > 48 * 1024 && conf < smem_bytes) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return fail(MMX_E_CUDA, "cudaFuncSetAttribute(%zu): %s", smem_bytes, cudaGetErrorString(e));
-        configured[dev] = smem_bytes;
+        conf = smem_bytes;
     }
     kern<<<grid, block, smem_bytes, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();

@@ -2,6 +2,7 @@
 #pragma once
 #include "mmx_launch.cuh"
 #include "mmx_mlp.cuh"
+#include "mmx_mlp_warp.cuh"
 
 namespace mmx {
 // ---------------------------------------------------------------------------------- MlpMixer block
@@ -60,5 +61,36 @@ static inline int plan_mlp_block(const MmxMlpBlockDesc* d, bool bwd, MlpDims* ou
     return fail(MMX_E_UNSUPPORTED, "MixerBlock tile does not fit shared memory (H=%d ch=%d)", d->H, d->ch);
 }
 
+// ---------------------------------------------------------------------------------- warp-per-sequence-pair variant
+constexpr int kWarpVariantWarps = 8;
+
+static inline bool mlp_warp_variant_ok(const MmxMlpBlockDesc* d) {
+    return d->T == 10 && d->tok == 20 && d->H <= 64 && d->ch <= 64 && !d->use_max_pooling && !env_int("MMX_MLP_V1", 0);
+}
+
+static inline int plan_mlp_block_warp(const MmxMlpBlockDesc* d, bool bwd, MlpDims* out, size_t* smem, int* grid, int* nwarp_out) {
+    if (d->B <= 0) return fail(MMX_E_INVALID, "non-positive dimension");
+    if (d->act != MMX_ACT_GELU && d->act != MMX_ACT_MISH) return fail(MMX_E_INVALID, "Unknown activation function type: %d", d->act);
+    if (d->use_se && d->se_hidden < 1) return fail(MMX_E_UNSUPPORTED, "seq_len // r_se == 0: empty SE bottleneck");
+    const DevInfo di = dev_info();
+    MlpDims m;
+    m.B = d->B; m.T = d->T; m.H = d->H; m.tok = d->tok; m.ch = d->ch; m.rr = d->use_se ? d->se_hidden : 0;
+    m.use_se = d->use_se; m.use_max = 0; m.training = d->training; m.site_base = d->block_index * 4;
+    m.S = kSPW; m.w_in_smem = 1;
+    int nwarp = env_int("MMX_MLP_WARPS", kWarpVariantWarps);
+    size_t bytes = 0;
+    for (; nwarp >= 2; --nwarp) {      // as many warps per CTA as the shared-memory scratch allows
+        bytes = (size_t)mlp_warp_smem(m, bwd, nwarp).total * 4;
+        if (bytes <= (size_t)di.max_smem) break;
+    }
+    if (nwarp < 2) return fail(MMX_E_UNSUPPORTED, "MixerBlock (warp variant) does not fit shared memory");
+    const int per_sm = imax(1, imin(4, (int)((di.max_smem + 1024) / (bytes + 1024))));
+    const int groups = (d->B + kSPW - 1) / kSPW;
+    const int max_warps = di.sms * per_sm * nwarp;
+    const int waves = (groups + max_warps - 1) / max_warps;
+    const int warps_needed = (groups + waves - 1) / waves;
+    *out = m; *smem = bytes; *grid = imax(1, (warps_needed + nwarp - 1) / nwarp); *nwarp_out = nwarp;
+    return MMX_OK;
+}
 
 }  // namespace mmx
