@@ -32,6 +32,18 @@ WORKLOADS = {
                family="mlp", B=4096, scale="h36m", loss_scale=1.0,
                cfg=dict(num_classes=66, num_blocks=4, hidden_dim=50, tokens_mlp_dim=20, channels_mlp_dim=50, seq_len=10,
                         pred_len=10, activation="mish", regularization=0.1, input_size=66, r_se=8, use_se=True)),
+    # SURVEY.md §8d K1 / BASELINE.json configs[0]: ConvMixer __main__ config (harmonic encoder 64), batch 256
+    "k1": dict(name="ConvMixer (train_mixer_h36m.py __main__ config), H36M xyz 10->25 frames (22 joints x 3), batch 256 per GPU",
+               family="conv", B=256, scale="h36m", loss_scale=1.0,
+               cfg=dict(num_blocks=4, dimPosIn=66, dimPosEmb=50, dimPosOut=66, in_nTP=10, out_nTP=25, conv_nChan=1,
+                        conv1_kernel_shape=(1, 3), conv1_stride=(1, 1), conv1_padding=(0, 1), mode_conv="twice", activation="mish",
+                        regularization=0.1, use_se=True, r_se=8)),
+    # the same ConvMixer at the K2 batch size (large-batch sweep, BASELINE.json configs[4])
+    "k1_b4096": dict(name="ConvMixer (train_mixer_h36m.py __main__ config), H36M xyz 10->25 frames, batch 4096 per GPU",
+                     family="conv", B=4096, scale="h36m", loss_scale=1.0,
+                     cfg=dict(num_blocks=4, dimPosIn=66, dimPosEmb=50, dimPosOut=66, in_nTP=10, out_nTP=25, conv_nChan=1,
+                              conv1_kernel_shape=(1, 3), conv1_stride=(1, 1), conv1_padding=(0, 1), mode_conv="twice", activation="mish",
+                              regularization=0.1, use_se=True, r_se=8)),
     # SURVEY.md §8d K4 / BASELINE.json configs[3] (AMASS-shaped), per-GPU batch 4096
     "k4": dict(name="MotionMixer MlpMixer+SE, AMASS-shaped 18 joints 10->25 frames, batch 4096 per GPU",
                family="mlp", B=4096, scale="amass", loss_scale=1000.0,
@@ -157,6 +169,7 @@ def run_ours(args, w):
     ge.build()
     from motionmixerconv_b200 import _lib as L
     from motionmixerconv_b200 import functional as F_
+    from motionmixerconv_b200.conv_mixer_model import ConvMixer
     from motionmixerconv_b200.mlp_mixer import MlpMixer
     from motionmixerconv_b200.train import TrainStep
     from oracle import mixer_torch as MT   # only for random_params (weight layout) and the cpu_baseline leg
@@ -170,8 +183,7 @@ def run_ours(args, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
-    assert w["family"] == "mlp"
-    model = MlpMixer(**w["cfg"])
+    model = MlpMixer(**w["cfg"]) if w["family"] == "mlp" else ConvMixer(**w["cfg"])
     model.load_state_dict(MT.random_params(w["family"], w["cfg"], 0), strict=True)
     model = model.to(dev).train()
     B = w["B"]
@@ -218,36 +230,50 @@ def run_ours(args, w):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_ms, t_e2e_ms = tt.tolist()
 
-    # ---- dominant kernel (MixerBlock backward) timed alone for the roofline ----
+    # ---- dominant kernel (block backward) timed alone for the roofline ----
     roof = None
     if rank == 0:
         import ctypes as C
         lib = L.load()
         pl = ts.plan
-        mb, tw, tg = pl.blocks[1]
-        d = pl._desc(mb, True)
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        c = w["cfg"]
+        if w["family"] == "mlp":
+            mb, tw, tg = pl.blocks[1]
+            d = pl._desc(mb, True)
+            call = lambda: L.check(lib, lib.mmx_mlp_block_bwd(C.byref(d), C.byref(tw), C.byref(tg), pl.acts[1].data_ptr(), pl.dact[0].data_ptr(),
+                                                              pl.dact[1].data_ptr(), st), "mmx_mlp_block_bwd")
+            tile = c["seq_len"] * c["hidden_dim"] * 4
+            kname = "mlp_block_bwd (MixerBlock backward, forward recomputed in-kernel)"
+            flops = B * 4 * 2 * c["seq_len"] * (2 * c["tokens_mlp_dim"] * c["hidden_dim"] + 2 * c["hidden_dim"] * c["channels_mlp_dim"])
+        else:
+            kind, mb, half, tw, tg = pl.ops[2]
+            d = pl._desc(mb, half, True)
+            call = lambda: L.check(lib, lib.mmx_conv_half_bwd(C.byref(d), C.byref(tw), C.byref(tg), pl.acts[2].data_ptr(), pl.dact[0].data_ptr(),
+                                                              pl.dact[1].data_ptr(), st), "mmx_conv_half_bwd")
+            tile = c["conv_nChan"] * c["in_nTP"] * c["dimPosEmb"] * 4
+            kname = "conv_half_bwd (one ConvMixerBlock half backward, forward recomputed in-kernel)"
+            kt, kp = mb.conv1.kernel
+            flops = B * 4 * 2 * c["conv_nChan"] ** 2 * kt * kp * c["in_nTP"] * c["dimPosEmb"]
         reps, tot = 20, 0.0
         for i in range(reps + 3):
             flush.add_(1.0)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            L.check(lib, lib.mmx_mlp_block_bwd(C.byref(d), C.byref(tw), C.byref(tg), pl.acts[1].data_ptr(), pl.dact[0].data_ptr(),
-                                               pl.dact[1].data_ptr(), st), "mmx_mlp_block_bwd")
+            call()
             e.record()
             torch.cuda.synchronize(dev)
             if i >= 3:
                 tot += s.elapsed_time(e)
         t_k = tot / reps
-        c = w["cfg"]
-        tile = c["seq_len"] * c["hidden_dim"] * 4
-        alg = B * 3 * tile                      # read saved block input + upstream grad, write input grad
+        alg = B * 3 * tile                      # read saved input + upstream grad, write input grad
         peak, which = peaks()
         ach = alg / (t_k * 1e-3) / 1e9
-        roof = {"kernel": "mlp_block_bwd (MixerBlock backward, forward recomputed in-kernel)", "bound": "hbm",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": which,
-                "algorithmic_bytes_per_launch": alg, "kernel_ms": t_k, "traffic": None,
-                "note": "fp32 SIMT; this shape (AI ~42 flop/B) sits above the fp32 CUDA-core ridge, see DESIGN.md"}
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12     # fp32 FMA pipe: 148 SMs x 128 lanes x 2 flop x 1.965 GHz (nominal)
+        roof = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "peak_source": which, "algorithmic_bytes_per_launch": alg, "kernel_ms": t_k, "traffic": None,
+                "fp32_tflops": flops / (t_k * 1e-3) / 1e12, "fp32_frac": flops / (t_k * 1e-3) / 1e12 / fp32_peak,
+                "note": "fp32 SIMT (1e-5 parity mode): the kernel is bound by the fp32 pipe / latency, not HBM — see DESIGN.md §4"}
 
     if rank != 0:
         if world > 1:
@@ -262,7 +288,7 @@ def run_ours(args, w):
         "config": {"workload": w["name"], "model": c, "per_gpu_batch": B, "global_batch": B * world,
                    "parallelism": "dp%d" % world, "optimizer": "Adam lr 1e-3 wd 1e-5 (fused, flat buffers)",
                    "l2": "512 MB L2 flush between timed iterations (outside the CUDA-event pairs)",
-                   "step": "CUDA graph: memset + embed + 4 block fwd + head + mpjpe + head bwd + 4 block bwd + embed bwd, [NCCL all-reduce], adam"},
+                   "step": "CUDA graph A: memset + embed/encoder + block kernels fwd + head + mpjpe + head bwd + block kernels bwd + embed/encoder bwd; [NCCL all-reduce of the flat bucket]; CUDA graph B: fused adam"},
         "e2e": {"value": world * B * args.steps / (t_e2e_ms * 1e-3), "unit": "sequences/s",
                 "h2d_bytes_per_step": x0.numel() * 4 + g0.numel() * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": t_e2e_ms / args.steps},
