@@ -105,6 +105,9 @@ typedef struct {
     float *ln_w, *ln_b;     /* LN1 / LN2 .weight, .bias                         [E]            */
     float *conv_w, *conv_b; /* conv1 / conv2 .conv.weight, .conv.bias           [C,C,kt,kp],[C]*/
     float *se_w1, *se_w2;   /* se.excitationBlock.0.weight [T/r,T], .2.weight [T,T/r]; null if !use_se */
+    float* bn_aff;          /* eval-mode BatchNorm2d (conv{1,2}.reg) folded to a per-channel affine applied after the
+                               activation: [scale[C] | shift[C]], scale = weight/sqrt(running_var+eps),
+                               shift = bias - running_mean*scale; null: no BatchNorm.  Ignored in grads tables. */
 } MmxConvHalfParams;
 
 typedef struct {
@@ -122,6 +125,25 @@ int mmx_conv_half_fwd(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, cons
 /* dx written; grads accumulated.  The forward is recomputed from x. */
 int mmx_conv_half_bwd(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, const MmxConvHalfParams* grads,
                       const float* x, const float* dy, float* dx, void* stream);
+
+/* Training-mode BatchNorm2d between the activation and the SE layer (regularization == -1, conv_mixer_model.py:115-116,
+ * 139-141) needs batch-global statistics, so a half runs as two passes each way; the per-channel vectors between the
+ * passes are computed by the caller from the sums (a handful of C-element tensor ops):
+ *   forward : bn_stats (LN -> conv; writes the pre-activation z [B,C,T,E]; sums[0:C] += sum act(z), sums[C:2C] += sum act(z)^2)
+ *             bn_apply (y = x + SE(act(z)*scale + shift))
+ *   backward: bn_bwd1  (SE backward; gd[b][t] = (gate, d pool); sums[0:C] += sum dR, sums[C:2C] += sum dR*xhat)
+ *             bn_bwd2  (dA = k1*(dR - k2 - xhat*k3); conv / LN backward without recomputing the conv; dx written)
+ * bn   = [scale | shift | xs | xo][C]:  R = act(z)*scale + shift,  xhat = act(z)*xs + xo  (xs = rstd, xo = -mean*rstd)
+ * coef = [k1 | k2 | k3][C]:            k1 = weight*rstd, k2 = mean(dR), k3 = mean(dR*xhat)
+ * SE gradients are accumulated by bn_bwd1, LN / conv gradients by bn_bwd2.  Mean squeeze only. */
+int mmx_conv_half_bn_stats(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, const float* x, float* z, double* sums, void* stream);
+int mmx_conv_half_bn_apply(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, const float* bn, const float* x, const float* z,
+                           float* y, void* stream);
+int mmx_conv_half_bn_bwd1(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, const MmxConvHalfParams* grads, const float* bn,
+                          const float* z, const float* dy, float* gd, double* sums, void* stream);
+int mmx_conv_half_bn_bwd2(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, const MmxConvHalfParams* grads, const float* bn,
+                          const float* coef, const float* x, const float* z, const float* dy, const float* gd, float* dx,
+                          void* stream);
 
 /* mode_conv="once": the second half of ConvMixerBlock.forward degenerates to y = x + se(x)  (or 2x without SE),
  * conv_mixer_model.py:259-263,287-292.  x, y: [B,C,T,E]; se weights may be null when !use_se. */

@@ -172,19 +172,27 @@ class ConvMixerBlock(nn.Module):
         return (cb.kernel, cb.pad, self.in_nTP // self.r_se if self.use_se else 0, self.activation, self.use_se,
                 self.use_max_pooling, self.training, 2 * self.block_index + half, p, seed, step)
 
-    def forward(self, x: torch.Tensor):
+    def _half(self, x, half, seed, step):
+        cb = self.conv1 if half == 0 else self.conv2
+        meta, params = self.half_meta(half, seed, step), self.half_params(half)
         if self.regularization == -1.0:
-            raise NotImplementedError(
-                "ConvMixerBlock with regularization=-1 (BatchNorm2d after the activation) is not built yet: batch "
-                "statistics need a two-pass split of the fused half (see DESIGN.md, scope)")
+            if self.use_se and self.use_max_pooling:
+                raise NotImplementedError("ConvMixerBlock: BatchNorm (regularization=-1) with use_max_pooling=True is not built "
+                                          "(the two-pass BatchNorm kernels implement the mean squeeze only)")
+            if self.training:
+                return F_.conv_half_bn(x, meta, cb.reg, params)
+            return F_.conv_half(x, meta, params, bn_aff=F_.bn_eval_affine(cb.reg))
+        return F_.conv_half(x, meta, params)
+
+    def forward(self, x: torch.Tensor):
         seed = step = 0
         if self.training and self.regularization > 0.0:
             seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
             step = self._calls
             self._calls = (self._calls + 1) & 0xFFFFFFFF
-        x = F_.conv_half(x, self.half_meta(0, seed, step), self.half_params(0))
+        x = self._half(x, 0, seed, step)
         if self.mode_conv == "twice":
-            return F_.conv_half(x, self.half_meta(1, seed, step), self.half_params(1))
+            return self._half(x, 1, seed, step)
         # mode_conv="once": LN2 / conv2 are Identity but self.se is still applied (conv_mixer_model.py:287-292)
         s1, s2 = self.se_weights()
         return F_.se_tail(x, self.in_nTP // self.r_se if self.use_se else 0, self.use_se, self.use_max_pooling, s1, s2)

@@ -92,6 +92,15 @@ MMX_D void warp_unlock(unsigned int* l, int lane) {
 #endif
 }
 
+// global double-precision accumulate (BatchNorm batch sums)
+MMX_D void red_add_f64(double* p, double v) {
+#if defined(MMX_HOST_EMU)
+    *p += v;
+#else
+    atomicAdd(p, v);
+#endif
+}
+
 MMX_HD int round_up(int x, int m) { return (x + m - 1) / m * m; }
 MMX_HD int imin(int a, int b) { return a < b ? a : b; }
 MMX_HD int imax(int a, int b) { return a > b ? a : b; }

@@ -24,8 +24,19 @@ struct ConvDims {
     int rr, S;            // SE hidden width (0: no SE), sequences per CTA tile
     int use_se, use_max, training;
     int site;             // dropout site of this half (2*block_index + half)
-    int x_in_smem;        // backward: X and dY tiles live in shared memory (else re-read from global; needs E%4==0)
+    int x_in_smem;        // backward: X and dY tiles live in shared memory (else re-read from global)
+    int bn_mode;          // 0: fused half.  forward 1: BatchNorm statistics pass (writes Z, accumulates batch sums).
+                          // backward 2: BatchNorm second pass (Z, gates and BN coefficients come from the first pass)
 };
+
+// BatchNorm2d (regularization == -1, conv_mixer_model.py:115-116,141) sits between the activation and the SE layer and
+// needs batch-global statistics, so a training half runs as
+//   forward : stats pass (LN -> conv -> Z to HBM, sum(A), sum(A^2) per channel)  ->  apply pass (mmx_conv_io.cuh)
+//   backward: pass 1 (SE backward, sum(dR), sum(dR*xhat) per channel; mmx_conv_io.cuh)  ->  pass 2 (this file: BN backward
+//             folded into the dZ phase, then the usual conv / LN backward; the conv is NOT recomputed, Z was saved)
+// The per-channel vectors are [scale | shift | xs | xo] (R = A*scale + shift, xhat = A*xs + xo) and
+// [k1 | k2 | k3] (dA = k1*(dR - k2 - xhat*k3)), computed from the sums by the host layer with tiny tensor ops.
+// In eval mode BN is a fixed per-channel affine: the fused kernels take it as an optional epilogue (`aff`).
 
 struct ConvHalfW {        // parameter (or gradient) pointers of one half, reference layouts
     float *ln_g, *ln_b;   // LN{1,2}.weight / bias                 [E]
@@ -40,7 +51,7 @@ struct ConvSmem {
     int CP, EW, PE, TP, EP, R, ST;
     int ln_g, ln_b, wtab, wtab2, cb, se1, se2;
     int part, part2, mean, rstd, pool, gate, amax, z, dq, dz, ds;
-    int a_lng, a_lnb, a_cb, a_se1, a_se2, a_cw;
+    int a_lng, a_lnb, a_cb, a_se1, a_se2, a_cw, a_bn;
     int bX, bD, nPad, zPad, bA, dN;
     int total;
 };
@@ -63,6 +74,7 @@ MMX_HD ConvSmem conv_smem(const ConvDims& d, bool bwd) {
     L.wtab = take(C * d.kT * d.kP * L.CP);
     L.wtab2 = bwd ? take(C * d.kT * d.kP * L.CP) : -1;
     L.cb = take(L.CP);
+    L.a_bn = take(16);   // BatchNorm statistics pass: per-CTA sum(A)[8], sum(A^2)[8]
     L.se1 = take(rr * T); L.se2 = take(T * rr);
     const int nred = imax(L.R, L.ST) * kParts;
     L.part = take(nred); L.part2 = take(nred);
@@ -355,6 +367,9 @@ struct ConvHalfFwdArgs {
     ConvHalfW w;
     const float* x;
     float* y;
+    const float* aff;   // optional eval-mode BatchNorm affine after the activation: [scale[C] | shift[C]] (null: none)
+    float* zout;        // bn_mode 1: pre-activation Z [B,C,T,E] (saved for the apply pass and the backward)
+    double* bnsum;      // bn_mode 1: [sum(A)[C] | sum(A^2)[C]] accumulated over the batch
 };
 
 template <int ACT, int CP>
@@ -372,16 +387,19 @@ MMX_D void conv_half_fwd_body(Exec& ex, const ConvHalfFwdArgs& a) {
     ex.phase([&](int tid) {
         conv_stage_tables(tid, nthr, sm, L, d, a.w.cw, false);
         for (int i = tid; i < CP; i += nthr) sm[L.cb + i] = i < C ? a.w.cb[i] : 0.0f;
+        for (int i = tid; i < 16; i += nthr) sm[L.a_bn + i] = 0.0f;
         copy_vec(tid, nthr, sm + L.ln_g, a.w.ln_g, E); copy_vec(tid, nthr, sm + L.ln_b, a.w.ln_b, E);
         if (d.use_se) { copy_vec(tid, nthr, sm + L.se1, a.w.se1, rr * T); copy_vec(tid, nthr, sm + L.se2, a.w.se2, T * rr); }
     });
+    const bool stats_pass = d.bn_mode == 1;
 
     const int ntiles = (d.B + S - 1) / S;
     for (int tile = ex.bid; tile < ntiles; tile += ex.nblk) {
         const long long seq0 = (long long)tile * S;
         const int ns = imin(S, d.B - (int)seq0), nr = ns * C * T;
         const float* xg = a.x + (size_t)seq0 * C * T * E;
-        float* yg = a.y + (size_t)seq0 * C * T * E;
+        float* yg = stats_pass ? nullptr : a.y + (size_t)seq0 * C * T * E;
+        float* zg = stats_pass ? a.zout + (size_t)seq0 * C * T * E : nullptr;
 
         ex.phase([&](int tid) {
             load_tile(tid, nthr, sm + L.bX, xg, nr, E, PE);
@@ -402,9 +420,42 @@ MMX_D void conv_half_fwd_body(Exec& ex, const ConvHalfFwdArgs& a) {
                                   const float b = sm[L.cb + co];
                                   float ks[4] = {1.0f, 1.0f, 1.0f, 1.0f};
                                   if (drop) dropout_quad(dr, d.site, ((uint64_t)(seq0 * C * T) + r) * E4 + (e >> 2), ks);
-                                  for (int k = 0; k < n; ++k) sm[L.bA + r * PE + e + k] = act_fwd<ACT>(v[k] + b) * ks[k];
+                                  const float sc = a.aff ? a.aff[co] : 1.0f, sh = a.aff ? a.aff[C + co] : 0.0f;
+                                  for (int k = 0; k < n; ++k) {
+                                      const float z = v[k] + b;
+                                      if (stats_pass) zg[(size_t)r * E + e + k] = z;
+                                      sm[L.bA + r * PE + e + k] = fmaf(act_fwd<ACT>(z) * ks[k], sc, sh);
+                                  }
                               });
         });
+        if (stats_pass) {
+            // per-channel batch sums of A = act(Z): row partials, then one (channel, part) owner per accumulator
+            ex.phase([&](int tid) {
+                for (int i = tid; i < nr * kParts; i += nthr) {
+                    const float* row = sm + L.bA + (i / kParts) * PE;
+                    const int p = i % kParts;
+                    float s1 = 0.0f, s2 = 0.0f;
+                    for (int h = 4 * p; h < E; h += 4 * kParts) {
+                        const int n = imin(4, E - h);
+                        for (int k = 0; k < n; ++k) { const float v = row[h + k]; s1 += v; s2 = fmaf(v, v, s2); }
+                    }
+                    sm[L.part + i] = s1; sm[L.part2 + i] = s2;
+                }
+            });
+            ex.phase([&](int tid) {
+                for (int i = tid; i < C * kParts; i += nthr) {
+                    const int co = i / kParts, p = i - co * kParts;
+                    float s1 = 0.0f, s2 = 0.0f;
+                    for (int s = 0; s < ns; ++s)
+                        for (int t = 0; t < T; ++t) {
+                            const int o = ((s * C + co) * T + t) * kParts + p;
+                            s1 += sm[L.part + o]; s2 += sm[L.part2 + o];
+                        }
+                    smem_add(sm + L.a_bn + co, s1); smem_add(sm + L.a_bn + 8 + co, s2);
+                }
+            });
+            continue;
+        }
         if (d.use_se) {
             ex.phase([&](int tid) {
                 for (int i = tid; i < ns * T * kParts; i += nthr) {
@@ -440,6 +491,13 @@ MMX_D void conv_half_fwd_body(Exec& ex, const ConvHalfFwdArgs& a) {
             }
         });
     }
+    if (stats_pass)
+        ex.phase([&](int tid) {
+            for (int i = tid; i < C; i += nthr) {
+                red_add_f64(a.bnsum + i, (double)sm[L.a_bn + i]);
+                red_add_f64(a.bnsum + C + i, (double)sm[L.a_bn + 8 + i]);
+            }
+        });
 }
 
 // ------------------------------------------------------------------------------------------
@@ -453,6 +511,12 @@ struct ConvHalfBwdArgs {
     const float* x;  // half input            [B,C,T,E]
     const float* dy; // dL/d(half output)
     float* dx;       // dL/d(half input)
+    const float* aff;   // fused mode: optional eval-mode BatchNorm affine [scale[C] | shift[C]]
+    // bn_mode 2 (BatchNorm backward, second pass):
+    const float* z;     // pre-activation saved by the forward statistics pass  [B,C,T,E]
+    const float* gd;    // per (sequence, frame): SE gate and d(pool) from backward pass 1   [B,T,2]
+    const float* bn;    // [scale | shift | xs | xo][C]
+    const float* coef;  // [k1 | k2 | k3][C]
 };
 
 template <int CP>
@@ -472,12 +536,20 @@ MMX_D void conv_half_bwd_body(Exec& ex, const ConvHalfBwdArgs& a) {
     const Dropout dr = resolve_dropout(a.dr);
     const bool drop = d.training && dr.thresh != 0u;
     const int nJB = (kP + 3) >> 2, n_items = C * kT * nJB, nsl_w = imax(1, nthr / n_items);
+    const bool bn2 = d.bn_mode == 2;
+    const bool se_here = d.use_se && !bn2;     // BatchNorm pass 2: the SE backward already ran in pass 1
+    const float* asc = sm + L.a_bn;            // eval-mode BatchNorm affine (identity when absent), staged below
+    const float* ash = sm + L.a_bn + 8;
 
     PerThread<ConvBwdRegs<CP>> regs(ex);
 
     ex.phase([&](int tid) {
         conv_stage_tables(tid, nthr, sm, L, d, a.w.cw, true);
         for (int i = tid; i < CP; i += nthr) { sm[L.cb + i] = i < C ? a.w.cb[i] : 0.0f; sm[L.a_cb + i] = 0.0f; }
+        for (int i = tid; i < 8; i += nthr) {
+            sm[L.a_bn + i] = (a.aff && i < C) ? a.aff[i] : 1.0f;
+            sm[L.a_bn + 8 + i] = (a.aff && i < C) ? a.aff[C + i] : 0.0f;
+        }
         copy_vec(tid, nthr, sm + L.ln_g, a.w.ln_g, E); copy_vec(tid, nthr, sm + L.ln_b, a.w.ln_b, E);
         zero_vec(tid, nthr, sm + L.a_lng, E); zero_vec(tid, nthr, sm + L.a_lnb, E);
         zero_vec(tid, nthr, sm + L.a_cw, C * C * kT * kP);
@@ -524,15 +596,23 @@ MMX_D void conv_half_bwd_body(Exec& ex, const ConvHalfBwdArgs& a) {
             }
         });
         ex.phase([&](int tid) {
-            conv_corr<CP, EW>(tid, nthr, sm + L.nPad, sm + L.wtab, C, C, kT, kP, TP, EP, ns, T, E,
-                              [&](int s, int co, int t, int e, const float* v, int n) {
-                                  float* zr = sm + L.zPad + ((size_t)(s * C + co) * TP + qT + t) * EP + qP + e;
-                                  const float b = sm[L.cb + co];
-                                  for (int k = 0; k < n; ++k) zr[k] = v[k] + b;
-                              });
+            if (bn2) {      // Z was saved by the forward statistics pass: no conv recompute
+                const float* zg = a.z + (size_t)seq0 * C * T * E;
+                for (int i = tid; i < nr * E; i += nthr) {
+                    const int r = i / E, e = i - r * E, sc = r / T, t = r - sc * T;
+                    sm[L.zPad + ((size_t)sc * TP + qT + t) * EP + qP + e] = zg[i];
+                }
+            } else {
+                conv_corr<CP, EW>(tid, nthr, sm + L.nPad, sm + L.wtab, C, C, kT, kP, TP, EP, ns, T, E,
+                                  [&](int s, int co, int t, int e, const float* v, int n) {
+                                      float* zr = sm + L.zPad + ((size_t)(s * C + co) * TP + qT + t) * EP + qP + e;
+                                      const float b = sm[L.cb + co];
+                                      for (int k = 0; k < n; ++k) zr[k] = v[k] + b;
+                                  });
+            }
         });
         // ---------------- SE: squeeze of A = drop(act(Z)) and dgate = sum dY*A, per (s,t) ----------------
-        if (d.use_se) {
+        if (se_here) {
             ex.phase([&](int tid) {
                 for (int i = tid; i < ns * T * kParts; i += nthr) {
                     const int st = i / kParts, p = i - st * kParts, s = st / T, t = st - s * T;
@@ -547,7 +627,7 @@ MMX_D void conv_half_bwd_body(Exec& ex, const ConvHalfBwdArgs& a) {
                             if (drop) dropout_quad(dr, d.site, ((uint64_t)(seq0 * C * T) + r) * E4 + (h >> 2), ks);
                             const int n = imin(4, E - h);
                             for (int k = 0; k < n; ++k) {
-                                const float av = act_fwd<ACT>(zr[h + k]) * ks[k];
+                                const float av = fmaf(act_fwd<ACT>(zr[h + k]) * ks[k], asc[c], ash[c]);
                                 dg = fmaf(dyr[h + k], av, dg);
                                 if (d.use_max) { if (av > pv) { pv = av; am = c * E + h + k; } }
                                 else pv += av;
@@ -577,7 +657,7 @@ MMX_D void conv_half_bwd_body(Exec& ex, const ConvHalfBwdArgs& a) {
                                 float ks[4] = {1.0f, 1.0f, 1.0f, 1.0f};
                                 if (drop) dropout_quad(dr, d.site, ((uint64_t)(seq0 * C * T) + r) * E4 + (h >> 2), ks);
                                 const int n = imin(4, E - h);
-                                for (int k = 0; k < n; ++k) dg = fmaf(dyr[h + k], act_fwd<ACT>(zr[h + k]) * ks[k], dg);
+                                for (int k = 0; k < n; ++k) dg = fmaf(dyr[h + k], fmaf(act_fwd<ACT>(zr[h + k]) * ks[k], asc[c], ash[c]), dg);
                             }
                         }
                         sm[L.part2 + i] = dg;
@@ -608,9 +688,10 @@ MMX_D void conv_half_bwd_body(Exec& ex, const ConvHalfBwdArgs& a) {
                 const int r = i / E4, q = i - r * E4, sc = r / T, t = r - sc * T, s = sc / C, c = sc - s * C;
                 float* zr = sm + L.zPad + ((size_t)sc * TP + qT + t) * EP + qP + 4 * q;
                 const float* dyr = dt + (size_t)r * xp + 4 * q;
-                const float g = d.use_se ? sm[L.gate + s * T + t] : 1.0f;
-                const float dsv = d.use_se ? sm[L.ds + s * T + t] : 0.0f;
-                const int amax = (d.use_se && d.use_max) ? (int)sm[L.amax + s * T + t] : -1;
+                float g = se_here ? sm[L.gate + s * T + t] : 1.0f;
+                float dsv = se_here ? sm[L.ds + s * T + t] : 0.0f;
+                if (bn2 && d.use_se) { g = a.gd[((size_t)(seq0 + s) * T + t) * 2]; dsv = a.gd[((size_t)(seq0 + s) * T + t) * 2 + 1]; }
+                const int amax = (se_here && d.use_max) ? (int)sm[L.amax + s * T + t] : -1;
                 float ks[4] = {1.0f, 1.0f, 1.0f, 1.0f};
                 if (drop) dropout_quad(dr, d.site, ((uint64_t)(seq0 * C * T) + r) * E4 + q, ks);
                 const int n = imin(4, E - 4 * q);
@@ -619,8 +700,14 @@ MMX_D void conv_half_bwd_body(Exec& ex, const ConvHalfBwdArgs& a) {
                     const float gp = act_fwd_grad<ACT>(zr[k], &av);
                     float da = dyr[k] * g;
                     if (d.use_se) {
-                        if (d.use_max) { if (c * E + 4 * q + k == amax) da += dsv; }
+                        if (se_here && d.use_max) { if (c * E + 4 * q + k == amax) da += dsv; }
                         else da = fmaf(dsv, invCE, da);
+                    }
+                    if (bn2) {          // BatchNorm backward: dA = k1 * (dR - mean(dR) - xhat * mean(dR*xhat))
+                        const float xh = fmaf(av, a.bn[2 * C + c], a.bn[3 * C + c]);
+                        da = a.coef[c] * (da - a.coef[C + c] - xh * a.coef[2 * C + c]);
+                    } else {
+                        da *= asc[c];
                     }
                     zr[k] = da * ks[k] * gp;
                 }
@@ -708,7 +795,7 @@ MMX_D void conv_half_bwd_body(Exec& ex, const ConvHalfBwdArgs& a) {
         for (int i = tid; i < C * C * kT * kP; i += nthr) red_add(a.g.cw + i, sm[L.a_cw + i]);
         for (int i = tid; i < C; i += nthr) red_add(a.g.cb + i, sm[L.a_cb + i]);
         for (int e = tid; e < E; e += nthr) { red_add(a.g.ln_g + e, sm[L.a_lng + e]); red_add(a.g.ln_b + e, sm[L.a_lnb + e]); }
-        if (d.use_se)
+        if (se_here)
             for (int i = tid; i < T * rr; i += nthr) { red_add(a.g.se1 + i, sm[L.a_se1 + i]); red_add(a.g.se2 + i, sm[L.a_se2 + i]); }
     });
 }

@@ -36,7 +36,7 @@ static inline int plan_conv_half(const MmxConvHalfDesc* d, bool bwd, ConvDims* o
     ConvDims m;
     m.B = d->B; m.C = d->C; m.T = d->T; m.E = d->E; m.kT = d->kt; m.kP = d->kp; m.pT = d->pad_t; m.pP = d->pad_p;
     m.rr = d->use_se ? d->se_hidden : 0; m.use_se = d->use_se; m.use_max = d->use_max_pooling; m.training = d->training;
-    m.site = d->site;
+    m.site = d->site; m.bn_mode = 0;
     const int two_cta_budget = (di.max_smem + 1024) / 2 - 2048;
     const int forced = env_int(bwd ? "MMX_CONV_S_BWD" : "MMX_CONV_S_FWD", 0);
     const int S0 = forced > 0 ? forced : imax(1, kConvTileElems / (d->C * d->T * d->E));

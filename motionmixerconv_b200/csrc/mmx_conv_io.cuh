@@ -763,3 +763,185 @@ MMX_D void conv_head_bwd_body(Exec& ex, const ConvHeadBwdArgs& a) {
 }
 
 }  // namespace mmx
+
+namespace mmx {
+
+// ==========================================================================================
+// BatchNorm halves (regularization == -1): the two passes that are NOT convolutions.
+//   apply (forward) :  R = act(Z)*scale[c] + shift[c] ;  y = x + SE(R)
+//   bwd1 (backward) :  gate, ds from SE backward with dgate = sum dy*R ;  dR = dy*gate + ds/(C*E) ;
+//                      sums[c] += sum dR ;  sums[C+c] += sum dR*xhat  (xhat = act(Z)*xs[c] + xo[c]) ;  gd[b][t] = (gate, ds)
+// Both stream x / Z / dy from global (elementwise + per-(sequence, frame) reductions; mean squeeze only).
+// ==========================================================================================
+struct BnPassDims { int B, C, T, E, rr, S, use_se, act; };
+struct BnPassSmem { int se1, se2, part, part2, pool, gate, z, dq, dz, ds, a_se1, a_se2, a_sum, bn, total; };
+MMX_HD BnPassSmem bn_pass_smem(const BnPassDims& d) {
+    BnPassSmem L;
+    const int rr = imax(d.rr, 1), ST = d.S * d.T;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += round_up(n, 4); return r; };
+    L.se1 = take(rr * d.T); L.se2 = take(d.T * rr);
+    L.part = take(ST * kParts); L.part2 = take(ST * kParts);
+    L.pool = take(ST); L.gate = take(ST); L.z = take(d.S * rr); L.dq = take(ST); L.dz = take(d.S * rr); L.ds = take(ST);
+    L.a_se1 = take(rr * d.T); L.a_se2 = take(d.T * rr); L.a_sum = take(16); L.bn = take(32);
+    L.total = o;
+    return L;
+}
+struct BnPassArgs {
+    BnPassDims d;
+    const float *se1, *se2;   // SE parameters (null without SE)
+    float *g_se1, *g_se2;     // SE gradient accumulators (bwd1)
+    const float* bn;          // [scale | shift | xs | xo][C]
+    const float* x;           // apply: half input
+    const float* z;           // pre-activation from the statistics pass
+    const float* dy;          // bwd1: upstream gradient
+    float* y;                 // apply: half output
+    float* gd;                // bwd1: [B,T,2] (gate, ds)
+    double* sums;             // bwd1: [sum dR | sum dR*xhat][C]
+};
+
+template <int ACT>
+MMX_D void bn_apply_fwd_body(Exec& ex, const BnPassArgs& a) {
+    const BnPassDims& d = a.d;
+    const BnPassSmem L = bn_pass_smem(d);
+    float* sm = ex.smem;
+    const int nthr = ex.nthr, C = d.C, T = d.T, E = d.E, S = d.S, rr = d.rr;
+    const float invCE = 1.0f / (float)(C * E);
+    ex.phase([&](int tid) {
+        if (d.use_se) { copy_vec(tid, nthr, sm + L.se1, a.se1, rr * T); copy_vec(tid, nthr, sm + L.se2, a.se2, T * rr); }
+        for (int i = tid; i < 4 * C; i += nthr) sm[L.bn + (i / C) * 8 + i % C] = a.bn[i];
+    });
+    const int ntiles = (d.B + S - 1) / S;
+    for (int tile = ex.bid; tile < ntiles; tile += ex.nblk) {
+        const long long seq0 = (long long)tile * S;
+        const int ns = imin(S, d.B - (int)seq0), nr = ns * C * T;
+        const float* xg = a.x + (size_t)seq0 * C * T * E;
+        const float* zg = a.z + (size_t)seq0 * C * T * E;
+        float* yg = a.y + (size_t)seq0 * C * T * E;
+        if (d.use_se) {
+            ex.phase([&](int tid) {
+                for (int i = tid; i < ns * T * kParts; i += nthr) {
+                    const int st = i / kParts, p = i - st * kParts, s = st / T, t = st - s * T;
+                    float acc = 0.0f;
+                    for (int c = 0; c < C; ++c) {
+                        const float sc = sm[L.bn + c], sh = sm[L.bn + 8 + c];
+                        const float* zr = zg + ((size_t)(s * C + c) * T + t) * E;
+                        for (int h = 4 * p; h < E; h += 4 * kParts) {
+                            const int n = imin(4, E - h);
+                            for (int k = 0; k < n; ++k) acc += fmaf(act_fwd<ACT>(zr[h + k]), sc, sh);
+                        }
+                    }
+                    sm[L.part + i] = acc;
+                }
+            });
+            ex.phase([&](int tid) {
+                for (int st = tid; st < ns * T; st += nthr) sm[L.pool + st] = sum_parts(sm + L.part + st * kParts) * invCE;
+            });
+            ex.phase([&](int tid) {
+                for (int st = tid; st < ns * T; st += nthr) {
+                    const int s = st / T, t = st - s * T;
+                    sm[L.gate + st] = se_excite(sm + L.se1, sm + L.se2, sm + L.pool + s * T, T, rr, t, nullptr);
+                }
+            });
+        }
+        ex.phase([&](int tid) {
+            for (int i = tid; i < nr * E; i += nthr) {
+                const int r = i / E, sc_ = r / T, t = r - sc_ * T, s = sc_ / C, c = sc_ - s * C;
+                const float g = d.use_se ? sm[L.gate + s * T + t] : 1.0f;
+                const float rv = fmaf(act_fwd<ACT>(zg[i]), sm[L.bn + c], sm[L.bn + 8 + c]);
+                yg[i] = fmaf(g, rv, xg[i]);
+            }
+        });
+    }
+}
+
+template <int ACT>
+MMX_D void bn_bwd1_body(Exec& ex, const BnPassArgs& a) {
+    const BnPassDims& d = a.d;
+    const BnPassSmem L = bn_pass_smem(d);
+    float* sm = ex.smem;
+    const int nthr = ex.nthr, C = d.C, T = d.T, E = d.E, S = d.S, rr = d.rr;
+    const float invCE = 1.0f / (float)(C * E);
+    ex.phase([&](int tid) {
+        if (d.use_se) {
+            copy_vec(tid, nthr, sm + L.se1, a.se1, rr * T); copy_vec(tid, nthr, sm + L.se2, a.se2, T * rr);
+            zero_vec(tid, nthr, sm + L.a_se1, rr * T); zero_vec(tid, nthr, sm + L.a_se2, T * rr);
+        }
+        for (int i = tid; i < 16; i += nthr) sm[L.a_sum + i] = 0.0f;
+        for (int i = tid; i < 4 * C; i += nthr) sm[L.bn + (i / C) * 8 + i % C] = a.bn[i];
+    });
+    const int ntiles = (d.B + S - 1) / S;
+    for (int tile = ex.bid; tile < ntiles; tile += ex.nblk) {
+        const long long seq0 = (long long)tile * S;
+        const int ns = imin(S, d.B - (int)seq0);
+        const float* zg = a.z + (size_t)seq0 * C * T * E;
+        const float* dyg = a.dy + (size_t)seq0 * C * T * E;
+        if (d.use_se) {
+            ex.phase([&](int tid) {      // squeeze of R and dgate = sum dy*R
+                for (int i = tid; i < ns * T * kParts; i += nthr) {
+                    const int st = i / kParts, p = i - st * kParts, s = st / T, t = st - s * T;
+                    float acc = 0.0f, dg = 0.0f;
+                    for (int c = 0; c < C; ++c) {
+                        const float sc = sm[L.bn + c], sh = sm[L.bn + 8 + c];
+                        const size_t off = ((size_t)(s * C + c) * T + t) * E;
+                        for (int h = 4 * p; h < E; h += 4 * kParts) {
+                            const int n = imin(4, E - h);
+                            for (int k = 0; k < n; ++k) {
+                                const float rv = fmaf(act_fwd<ACT>(zg[off + h + k]), sc, sh);
+                                acc += rv; dg = fmaf(dyg[off + h + k], rv, dg);
+                            }
+                        }
+                    }
+                    sm[L.part + i] = acc; sm[L.part2 + i] = dg;
+                }
+            });
+            ex.phase([&](int tid) {
+                for (int st = tid; st < ns * T; st += nthr) {
+                    sm[L.pool + st] = sum_parts(sm + L.part + st * kParts) * invCE;
+                    sm[L.dq + st] = sum_parts(sm + L.part2 + st * kParts);
+                }
+            });
+            ex.phase([&](int tid) {
+                for (int st = tid; st < ns * T; st += nthr) {
+                    const int s = st / T, t = st - s * T;
+                    sm[L.gate + st] = se_excite(sm + L.se1, sm + L.se2, sm + L.pool + s * T, T, rr, t, sm + L.z + s * rr);
+                }
+            });
+            se_bwd_phases(ex, sm, T, rr, ns, L.se1, L.se2, L.dq, L.dz, L.gate, L.pool, L.z, L.ds, L.a_se1, L.a_se2);
+        }
+        // dR = dy*gate + ds/(C*E): per-channel sums of dR and dR*xhat; (gate, ds) saved for pass 2
+        ex.phase([&](int tid) {
+            for (int st = tid; st < ns * T; st += nthr) {
+                a.gd[((size_t)seq0 * T + st) * 2] = d.use_se ? sm[L.gate + st] : 1.0f;
+                a.gd[((size_t)seq0 * T + st) * 2 + 1] = d.use_se ? sm[L.ds + st] : 0.0f;
+            }
+            for (int i = tid; i < ns * C * T * kParts; i += nthr) {
+                const int r = i / kParts, p = i - r * kParts, sc_ = r / T, t = r - sc_ * T, s = sc_ / C, c = sc_ - s * C;
+                const float g = d.use_se ? sm[L.gate + s * T + t] : 1.0f;
+                const float dsv = d.use_se ? sm[L.ds + s * T + t] * invCE : 0.0f;
+                const float xs = sm[L.bn + 16 + c], xo = sm[L.bn + 24 + c];
+                const size_t off = (size_t)r * E;
+                float s1 = 0.0f, s2 = 0.0f;
+                for (int h = 4 * p; h < E; h += 4 * kParts) {
+                    const int n = imin(4, E - h);
+                    for (int k = 0; k < n; ++k) {
+                        const float dr_ = fmaf(dyg[off + h + k], g, dsv);
+                        const float xh = fmaf(act_fwd<ACT>(zg[off + h + k]), xs, xo);
+                        s1 += dr_; s2 = fmaf(dr_, xh, s2);
+                    }
+                }
+                smem_add(sm + L.a_sum + c, s1); smem_add(sm + L.a_sum + 8 + c, s2);
+            }
+        });
+    }
+    ex.phase([&](int tid) {
+        for (int i = tid; i < C; i += nthr) {
+            red_add_f64(a.sums + i, (double)sm[L.a_sum + i]);
+            red_add_f64(a.sums + C + i, (double)sm[L.a_sum + 8 + i]);
+        }
+        if (d.use_se)
+            for (int i = tid; i < T * rr; i += nthr) { red_add(a.g_se1 + i, sm[L.a_se1 + i]); red_add(a.g_se2 + i, sm[L.a_se2 + i]); }
+    });
+}
+
+}  // namespace mmx

@@ -214,11 +214,13 @@ def mpjpe_error(batch_pred, batch_gt):
 # ------------------------------------------------------------------------------------------------
 # ConvMixer (conv_mixer_model.py, positional_encoder.py)
 # ------------------------------------------------------------------------------------------------
-def conv_half_table(tensors):
-    """tensors: (ln_w, ln_b, conv_w, conv_b, se_w1, se_w2) — the order of ``MmxConvHalfParams``."""
+def conv_half_table(tensors, bn_aff=None):
+    """tensors: (ln_w, ln_b, conv_w, conv_b, se_w1, se_w2) — the order of ``MmxConvHalfParams``; ``bn_aff``: optional
+    eval-mode BatchNorm affine [scale | shift] (2C floats)."""
     t = L.MmxConvHalfParams()
     for f, v in zip(("ln_w", "ln_b", "conv_w", "conv_b", "se_w1", "se_w2"), tensors):
         setattr(t, f, _p(v))
+    t.bn_aff = _p(bn_aff)
     return t
 
 
@@ -260,9 +262,128 @@ class _ConvHalf(torch.autograd.Function):
         return (dx, None, *grads)
 
 
-def conv_half(x, meta, params):
-    """meta = (kernel, pad, se_hidden, act, use_se, use_max, training, site, p, seed, step)."""
-    return _ConvHalf.apply(x, meta, *params)
+def conv_half(x, meta, params, bn_aff=None):
+    """meta = (kernel, pad, se_hidden, act, use_se, use_max, training, site, p, seed, step).  ``bn_aff``: eval-mode
+    BatchNorm folded to [scale | shift] (treated as a constant: no gradient flows to the BN parameters in eval mode)."""
+    if bn_aff is None:
+        return _ConvHalf.apply(x, meta, *params)
+    return _ConvHalfAffine.apply(x, meta, bn_aff, *params)
+
+
+class _ConvHalfAffine(torch.autograd.Function):
+    """The fused half with a constant per-channel affine after the activation (BatchNorm2d in eval mode)."""
+
+    @staticmethod
+    def forward(ctx, x, meta, aff, *params):
+        x, aff = _chk(x, "x"), _chk(aff, "bn affine")
+        params = [None if q is None else _chk(q, "parameter") for q in params]
+        B, C, T, E = x.shape
+        desc = conv_half_desc(B, C, T, E, *meta)
+        y = torch.empty_like(x)
+        with torch.cuda.device_of(x):
+            _call("mmx_conv_half_fwd", C_.byref(desc), C_.byref(conv_half_table(params, aff)), _p(x), _p(y), _stream())
+        ctx.save_for_backward(x, aff, *[q for q in params if q is not None])
+        ctx.has = [q is not None for q in params]
+        ctx.meta = meta
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, aff, *rest = ctx.saved_tensors
+        it = iter(rest)
+        params = [next(it) if h else None for h in ctx.has]
+        dy = _chk(dy, "grad")
+        B, C, T, E = x.shape
+        desc = conv_half_desc(B, C, T, E, *ctx.meta)
+        grads = _zeros_like_many(params)
+        dx = torch.empty_like(x)
+        with torch.cuda.device_of(x):
+            _call("mmx_conv_half_bwd", C_.byref(desc), C_.byref(conv_half_table(params, aff)), C_.byref(conv_half_table(grads)),
+                  _p(x), _p(dy), _p(dx), _stream())
+        return (dx, None, None, *grads)
+
+
+# ---- training-mode BatchNorm2d between the activation and the SE layer (regularization == -1) ----------------
+BN_EPS = 1e-5
+
+
+def bn_forward_passes(desc, tw, x, z, y, sums, bn_w, bn_b, running_mean, running_var, num_batches_tracked, momentum=0.1):
+    """statistics pass -> per-channel vectors (tensor ops on C elements) -> apply pass.  Updates the running statistics
+    as nn.BatchNorm2d does (biased variance to normalise, unbiased for the running estimate).  Returns bn = [scale|shift|xs|xo]."""
+    B, Cn, T, E = x.shape
+    n = B * T * E
+    st = _stream()
+    sums.zero_()
+    _call("mmx_conv_half_bn_stats", C_.byref(desc), C_.byref(tw), _p(x), _p(z), _p(sums), st)
+    mean = sums[:Cn] / n
+    var = (sums[Cn:] / n - mean * mean).clamp_min_(0.0)
+    rstd = torch.rsqrt(var + BN_EPS)
+    scale = bn_w.double() * rstd
+    bn = torch.cat([scale, bn_b.double() - mean * scale, rstd, -mean * rstd]).float()
+    _call("mmx_conv_half_bn_apply", C_.byref(desc), C_.byref(tw), _p(bn), _p(x), _p(z), _p(y), st)
+    with torch.no_grad():
+        running_mean.mul_(1.0 - momentum).add_(mean.float(), alpha=momentum)
+        running_var.mul_(1.0 - momentum).add_((var * (n / max(n - 1, 1))).float(), alpha=momentum)
+        num_batches_tracked.add_(1)
+    return bn
+
+
+def bn_backward_passes(desc, tw, tg, x, z, dy, dx, bn, gd, sums, n):
+    """pass 1 (SE backward + batch sums) -> coefficients -> pass 2 (BN / conv / LN backward).  Returns (d bn.weight, d bn.bias)."""
+    Cn = bn.numel() // 4
+    st = _stream()
+    sums.zero_()
+    _call("mmx_conv_half_bn_bwd1", C_.byref(desc), C_.byref(tw), C_.byref(tg), _p(bn), _p(z), _p(dy), _p(gd), _p(sums), st)
+    coef = torch.cat([bn[:Cn].double(), sums[:Cn] / n, sums[Cn:] / n]).float()
+    _call("mmx_conv_half_bn_bwd2", C_.byref(desc), C_.byref(tw), C_.byref(tg), _p(bn), _p(coef), _p(x), _p(z), _p(dy), _p(gd), _p(dx), st)
+    return sums[Cn:].float(), sums[:Cn].float()
+
+
+class _ConvHalfBN(torch.autograd.Function):
+    """One half with training-mode BatchNorm2d: y = x + SE(BN(act(conv(LN(x)))))  (conv_mixer_model.py:139-141,279-292)."""
+
+    @staticmethod
+    def forward(ctx, x, meta, bn_w, bn_b, running_mean, running_var, num_batches_tracked, *params):
+        x = _chk(x, "x")
+        params = [None if q is None else _chk(q, "parameter") for q in params]
+        bn_w, bn_b = _chk(bn_w, "bn weight"), _chk(bn_b, "bn bias")
+        B, C, T, E = x.shape
+        desc = conv_half_desc(B, C, T, E, *meta)
+        z, y = torch.empty_like(x), torch.empty_like(x)
+        sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        with torch.cuda.device_of(x):
+            bn = bn_forward_passes(desc, conv_half_table(params), x, z, y, sums, bn_w, bn_b, running_mean, running_var, num_batches_tracked)
+        ctx.save_for_backward(x, z, bn, *[q for q in params if q is not None])
+        ctx.has = [q is not None for q in params]
+        ctx.meta = meta
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, z, bn, *rest = ctx.saved_tensors
+        it = iter(rest)
+        params = [next(it) if h else None for h in ctx.has]
+        dy = _chk(dy, "grad")
+        B, C, T, E = x.shape
+        desc = conv_half_desc(B, C, T, E, *ctx.meta)
+        grads = _zeros_like_many(params)
+        dx = torch.empty_like(x)
+        gd = torch.empty(B, T, 2, dtype=torch.float32, device=x.device)
+        sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        with torch.cuda.device_of(x):
+            dw, db = bn_backward_passes(desc, conv_half_table(params), conv_half_table(grads), x, z, dy, dx, bn, gd, sums, B * T * E)
+        return (dx, None, dw, db, None, None, None, *grads)
+
+
+def conv_half_bn(x, meta, bn_module, params):
+    return _ConvHalfBN.apply(x, meta, bn_module.weight, bn_module.bias, bn_module.running_mean, bn_module.running_var,
+                             bn_module.num_batches_tracked, *params)
+
+
+def bn_eval_affine(bn_module):
+    """BatchNorm2d in eval mode as [scale | shift] (2C floats)."""
+    scale = bn_module.weight.detach() * torch.rsqrt(bn_module.running_var + bn_module.eps)
+    return torch.cat([scale, bn_module.bias.detach() - bn_module.running_mean * scale]).contiguous()
 
 
 class _SeTail(torch.autograd.Function):

@@ -152,11 +152,18 @@ class _ConvMixerPlan:
         self.enc_desc = L.MmxEncoderDesc(B, T, D, E, C, self.Hn)
         # ops in execution order: ("half", block, half, params table, grads table) | ("tail", block, se ptrs)
         self.ops = []
+        self.bn = {}                      # op index -> BatchNorm state of that half (regularization == -1)
         for mb in model.Mixer_Block:
-            if mb.regularization == -1.0:
-                raise NotImplementedError("TrainStep: BatchNorm (regularization=-1) ConvMixerBlocks are not built yet")
             for half in ((0, 1) if mb.mode_conv == "twice" else (0,)):
                 hp = mb.half_params(half)
+                if mb.regularization == -1.0:
+                    if mb.use_se and mb.use_max_pooling:
+                        raise NotImplementedError("TrainStep: BatchNorm with use_max_pooling=True is not built")
+                    reg = (mb.conv1 if half == 0 else mb.conv2).reg
+                    self.bn[len(self.ops)] = dict(
+                        reg=reg, z=torch.empty(B, C, T, E, device=dev), gd=torch.empty(B, T, 2, device=dev),
+                        sums=torch.zeros(2 * C, dtype=torch.float64, device=dev), bn=None,
+                        gw=flat.grad_of(reg.weight), gb=flat.grad_of(reg.bias))
                 self.ops.append(("half", mb, half, F_.conv_half_table(hp), F_.conv_half_table([flat.grad_of(q) for q in hp])))
             if mb.mode_conv != "twice":
                 s1, s2 = mb.se_weights()
@@ -187,7 +194,20 @@ class _ConvMixerPlan:
         L.check(lib, lib.mmx_pose_encoder_fwd(C.byref(self.enc_desc), C.byref(self.enc_w), _p(self.x), _p(self.m), _p(self.acts[0]), st),
                 "mmx_pose_encoder_fwd")
         for i, (kind, mb, half, tw, _) in enumerate(self.ops):
-            if kind == "half":
+            if kind == "half" and i in self.bn:
+                b = self.bn[i]
+                d = self._desc(mb, half, training)
+                if training:
+                    reg = b["reg"]
+                    b["bn"] = F_.bn_forward_passes(d, tw, self.acts[i], b["z"], self.acts[i + 1], b["sums"], reg.weight, reg.bias,
+                                                   reg.running_mean, reg.running_var, reg.num_batches_tracked)
+                else:
+                    aff = F_.bn_eval_affine(b["reg"])
+                    hp = mb.half_params(half)
+                    L.check(lib, lib.mmx_conv_half_fwd(C.byref(d), C.byref(F_.conv_half_table(hp, aff)), _p(self.acts[i]), _p(self.acts[i + 1]), st),
+                            "mmx_conv_half_fwd")
+                    self._keep = aff
+            elif kind == "half":
                 d = self._desc(mb, half, training)
                 L.check(lib, lib.mmx_conv_half_fwd(C.byref(d), C.byref(tw), _p(self.acts[i]), _p(self.acts[i + 1]), st), "mmx_conv_half_fwd")
             else:
@@ -202,7 +222,14 @@ class _ConvMixerPlan:
         for i in reversed(range(len(self.ops))):
             kind, mb, half, tw, tg = self.ops[i]
             nxt = self.dact[1] if cur is self.dact[0] else self.dact[0]
-            if kind == "half":
+            if kind == "half" and i in self.bn:
+                b = self.bn[i]
+                d = self._desc(mb, half, True)
+                Bn, Cn, Tn, En = self.acts[i].shape
+                dw, db = F_.bn_backward_passes(d, tw, tg, self.acts[i], b["z"], cur, nxt, b["bn"], b["gd"], b["sums"], Bn * Tn * En)
+                b["gw"].add_(dw)
+                b["gb"].add_(db)
+            elif kind == "half":
                 d = self._desc(mb, half, True)
                 L.check(lib, lib.mmx_conv_half_bwd(C.byref(d), C.byref(tw), C.byref(tg), _p(self.acts[i]), _p(cur), _p(nxt), st), "mmx_conv_half_bwd")
             else:
@@ -318,14 +345,15 @@ class TrainStep:
         # warm-up on a side stream (first launches set kernel attributes), then capture
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
-        saved = [b.clone() for b in (self.flat.p, self.flat.m, self.flat.v, self.hyper, self.step_dev)]
+        state = [self.flat.p, self.flat.m, self.flat.v, self.hyper, self.step_dev, *self.model.buffers()]   # incl. BN running stats
+        saved = [b.clone() for b in state]
         with torch.cuda.stream(s):
             self._fwd_bwd()
             self._adam()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize(self.device)
         with torch.no_grad():
-            for b, sv in zip((self.flat.p, self.flat.m, self.flat.v, self.hyper, self.step_dev), saved):
+            for b, sv in zip(state, saved):
                 b.copy_(sv)
         self.graph_a = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_a):

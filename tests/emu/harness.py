@@ -193,6 +193,8 @@ class EmuConvMixer:
         self.act = L.MMX_ACT[c.get("activation", "gelu")]
         self.twice = c.get("mode_conv", "twice") == "twice"
         self.k1, self.pad1, self.k2, self.pad2 = conv_geometry(c)
+        self.bn = c.get("regularization", 0) == -1.0
+        self.running = {k: np.array(v, copy=True) for k, v in params.items() if "running_" in k or "num_batches" in k}
 
     def _half_tables(self, i, half, src):
         t = L.MmxConvHalfParams()
@@ -235,11 +237,34 @@ class EmuConvMixer:
         call("mmx_pose_encoder_fwd", _byref(ed), _byref(self._enc(self.p)), ptr(x), ptr(self.m), ptr(y), None)
         self.acts = [y]           # inputs of every half / tail, in execution order
         self.ops = []
+        self.bn_saved, self._keep = {}, []
         for i in range(self.cfg["num_blocks"]):
             for half in ((0, 1) if self.twice else (0,)):
                 out = np.empty_like(y)
-                call("mmx_conv_half_fwd", _byref(self._half_desc(i, half, B)), _byref(self._half_tables(i, half, self.p)),
-                     ptr(self.acts[-1]), ptr(out), None)
+                desc, tw = self._half_desc(i, half, B), self._half_tables(i, half, self.p)
+                if self.bn and self.training:
+                    pre = "Mixer_Block.%d.conv%d.reg." % (i, half + 1)
+                    z = np.empty_like(y)
+                    sums = np.zeros(2 * C, np.float64)
+                    call("mmx_conv_half_bn_stats", _byref(desc), _byref(tw), ptr(self.acts[-1]), ptr(z), sums.ctypes.data, None)
+                    n = B * T * E
+                    mean = sums[:C] / n
+                    var = np.maximum(sums[C:] / n - mean * mean, 0.0)
+                    rstd = 1.0 / np.sqrt(var + 1e-5)
+                    scale = self.p[pre + "weight"].astype(np.float64) * rstd
+                    bn = f32(np.concatenate([scale, self.p[pre + "bias"] - mean * scale, rstd, -mean * rstd]))
+                    call("mmx_conv_half_bn_apply", _byref(desc), _byref(tw), ptr(bn), ptr(self.acts[-1]), ptr(z), ptr(out), None)
+                    self.running[pre + "running_mean"] = 0.9 * self.running[pre + "running_mean"] + 0.1 * mean
+                    self.running[pre + "running_var"] = 0.9 * self.running[pre + "running_var"] + 0.1 * var * n / (n - 1)
+                    self.bn_saved[(i, half)] = (z, bn)
+                else:
+                    if self.bn:
+                        pre = "Mixer_Block.%d.conv%d.reg." % (i, half + 1)
+                        sc = self.p[pre + "weight"] / np.sqrt(self.running[pre + "running_var"] + 1e-5)
+                        aff = f32(np.concatenate([sc, self.p[pre + "bias"] - self.running[pre + "running_mean"] * sc]))
+                        self._keep.append(aff)
+                        tw.bn_aff = ptr(aff)
+                    call("mmx_conv_half_fwd", _byref(desc), _byref(tw), ptr(self.acts[-1]), ptr(out), None)
                 self.acts.append(out)
                 self.ops.append(("half", i, half))
             if not self.twice:
@@ -266,7 +291,20 @@ class EmuConvMixer:
         for n in reversed(range(len(self.ops))):
             kind, i, half = self.ops[n]
             dx = np.empty_like(d_act)
-            if kind == "half":
+            if kind == "half" and self.bn:
+                desc, tw, tg = self._half_desc(i, half, B), self._half_tables(i, half, self.p), self._half_tables(i, half, g)
+                z, bn = self.bn_saved[(i, half)]
+                pre = "Mixer_Block.%d.conv%d.reg." % (i, half + 1)
+                gd = np.empty((B, T, 2), np.float32)
+                sums = np.zeros(2 * C, np.float64)
+                call("mmx_conv_half_bn_bwd1", _byref(desc), _byref(tw), _byref(tg), ptr(bn), ptr(z), ptr(d_act), ptr(gd), sums.ctypes.data, None)
+                nel = B * T * E
+                coef = f32(np.concatenate([bn[:C].astype(np.float64), sums[:C] / nel, sums[C:] / nel]))
+                call("mmx_conv_half_bn_bwd2", _byref(desc), _byref(tw), _byref(tg), ptr(bn), ptr(coef), ptr(self.acts[n]), ptr(z),
+                     ptr(d_act), ptr(gd), ptr(dx), None)
+                g[pre + "weight"] += sums[C:].astype(np.float32)
+                g[pre + "bias"] += sums[:C].astype(np.float32)
+            elif kind == "half":
                 call("mmx_conv_half_bwd", _byref(self._half_desc(i, half, B)), _byref(self._half_tables(i, half, self.p)),
                      _byref(self._half_tables(i, half, g)), ptr(self.acts[n]), ptr(d_act), ptr(dx), None)
             else:
@@ -281,7 +319,7 @@ class EmuConvMixer:
         call("mmx_pose_encoder_bwd", _byref(ed), _byref(self._enc(self.p)), _byref(self._enc(g)), ptr(self.x), ptr(self.m),
              ptr(d_act), ptr(dm), ptr(dxin), None)
         for k in list(g):
-            if ".se2." in k:          # alias of .se. in the reference state_dict
+            if ".se2." in k or "running_" in k:          # aliases of .se. in the reference state_dict; BN buffers
                 g.pop(k)
         g.pop("encoder.frequencies", None)
         return g, dxin

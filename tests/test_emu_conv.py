@@ -12,7 +12,7 @@ from tests.emu import harness as H
 from tests.golden_util import Golden, check_close, golden_cases, grad_scale
 
 TOL = 1e-5
-CONV_CASES = [c for c in golden_cases("conv") if not c.endswith("_bn")]
+CONV_CASES = golden_cases("conv")     # includes conv_k3_bn: BatchNorm2d halves (two-pass kernels)
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
@@ -35,6 +35,13 @@ def test_emulated_kernels_match_golden(case):
     loss, dpred = H.mpjpe(pred, gt)
     assert abs(loss - float(l64)) <= TOL * abs(float(l64))
     grads, dx = m.backward(dpred)
+    if m.bn:      # running statistics follow nn.BatchNorm2d (momentum 0.1, unbiased variance); eval mode uses them
+        for k, v in m.running.items():
+            if "num_batches" not in k:
+                np.testing.assert_allclose(v, o64.p[k], rtol=1e-5, atol=1e-7)
+        me = H.EmuConvMixer(g.cfg, {**g.params, **{k: o64.p[k] for k in m.running}}, training=False)
+        pe = O.ConvMixerOracle(g.cfg, {**g.params, **{k: o64.p[k] for k in m.running}}, dtype=np.float64).forward(x, training=False)
+        check_close("pred_eval", me.forward(x), pe.astype(np.float32), pe, rtol=TOL)
     floor = 1e-6 * grad_scale(g32)
     for k in O.trainable_keys(g.params):
         check_close("grad " + k, grads[k], g32[k], g64[k], rtol=TOL, atol=floor)

@@ -134,3 +134,51 @@ def test_dropout_training_mode():
     with torch.no_grad():
         e = model(x).cpu().numpy()
     np.testing.assert_allclose(e, g.pred_eval, rtol=0, atol=1e-5 * np.abs(g.pred_eval).max())
+
+
+# ---- BatchNorm2d halves (regularization == -1, the Optuna "production" setting) ----------------
+def test_batchnorm_golden_train_and_eval():
+    g = Golden("conv_k3_bn")
+    model = _model(g.cfg, g.params).train()
+    pred, loss, grads, dx = _run(model, g.x, g.gt)
+    o64 = O.ConvMixerOracle(g.cfg, g.params, dtype=np.float64)
+    p64 = o64.forward(g.x)
+    _, dp64 = O.mpjpe(p64, g.gt.astype(np.float64))
+    g64, dx64 = o64.backward(dp64)
+    check_close("pred", pred, g.pred, p64, rtol=TOL)
+    assert abs(loss - g.loss) <= TOL * abs(g.loss)
+    floor = 1e-6 * grad_scale(g.grads)
+    for k, want in g.grads.items():
+        if ".se2." in k:
+            continue
+        check_close("grad " + k, grads[k], want, g64[k], rtol=TOL, atol=floor)
+    check_close("dx", dx, g.dx, dx64, rtol=TOL, atol=1e-6 * float(np.abs(g.dx).max()))
+    sd = model.state_dict()
+    for k in sd:                                    # running statistics after ONE training forward == the reference's
+        if "running_" in k:
+            np.testing.assert_allclose(sd[k].cpu().numpy(), o64.p[k], rtol=1e-5, atol=1e-7, err_msg=k)
+        if "num_batches_tracked" in k:
+            assert int(sd[k]) == int(g.params[k]) + 1
+    # eval mode uses the running statistics (folded into a per-channel affine inside the fused kernel)
+    ref = O.ConvMixerOracle(g.cfg, {k: v.cpu().numpy() for k, v in sd.items()}, dtype=np.float64)
+    pe64 = ref.forward(g.x, training=False)
+    model.eval()
+    with torch.no_grad():
+        pe = model(torch.from_numpy(g.x).cuda()).cpu().numpy()
+    check_close("pred_eval", pe, pe64.astype(np.float32), pe64, rtol=TOL)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_batchnorm_trainstep_three_adam_steps(use_graph):
+    from motionmixerconv_b200.train import TrainStep
+    g = Golden("conv_k3_bn")
+    model = _model(g.cfg, g.params).train()
+    ts = TrainStep(model, lr=1e-3, weight_decay=1e-5, use_cuda_graph=use_graph)
+    x, gt = torch.from_numpy(g.x).cuda(), torch.from_numpy(g.gt).cuda()
+    losses = [float(ts.step(x, gt)) for _ in range(3)]
+    np.testing.assert_allclose(losses, g.losses, rtol=5e-5)
+    sd = model.state_dict()
+    assert int(sd["Mixer_Block.0.conv1.reg.num_batches_tracked"]) == 3
+    for k in g.params3:
+        if "running_" in k:
+            np.testing.assert_allclose(sd[k].cpu().numpy(), g.params3[k], rtol=2e-4, atol=1e-6, err_msg=k)
