@@ -44,6 +44,13 @@ WORKLOADS = {
                      cfg=dict(num_blocks=4, dimPosIn=66, dimPosEmb=50, dimPosOut=66, in_nTP=10, out_nTP=25, conv_nChan=1,
                               conv1_kernel_shape=(1, 3), conv1_stride=(1, 1), conv1_padding=(0, 1), mode_conv="twice", activation="mish",
                               regularization=0.1, use_se=True, r_se=8)),
+    # SURVEY.md §8d K3 / BASELINE.json configs[2]: ConvMixer AIS autoregressive config (BatchNorm, C=4, E=192, 5x9 / 9x5
+    # kernels, 6 blocks), ONE 10 -> 5 pass of the rollout, batch 256
+    "k3": dict(name="ConvMixer AIS autoregressive config (BatchNorm, C=4, E=192, k=(5,9)), 10->5 frames (11 joints x 3), batch 256 per GPU",
+               family="conv", B=256, scale="ais", loss_scale=1.0,
+               cfg=dict(num_blocks=6, dimPosIn=33, dimPosEmb=192, dimPosOut=33, in_nTP=10, out_nTP=5, conv_nChan=4,
+                        conv1_kernel_shape=(5, 9), mode_conv="twice", activation="mish", regularization=-1.0, use_se=True, r_se=8,
+                        encoder_n_harmonic_functions=0, encoder_omega0=0)),
     # SURVEY.md §8d K4 / BASELINE.json configs[3] (AMASS-shaped), per-GPU batch 4096
     "k4": dict(name="MotionMixer MlpMixer+SE, AMASS-shaped 18 joints 10->25 frames, batch 4096 per GPU",
                family="mlp", B=4096, scale="amass", loss_scale=1000.0,
@@ -249,8 +256,15 @@ def run_ours(args, w):
         else:
             kind, mb, half, tw, tg = pl.ops[2]
             d = pl._desc(mb, half, True)
-            call = lambda: L.check(lib, lib.mmx_conv_half_bwd(C.byref(d), C.byref(tw), C.byref(tg), pl.acts[2].data_ptr(), pl.dact[0].data_ptr(),
-                                                              pl.dact[1].data_ptr(), st), "mmx_conv_half_bwd")
+            if 2 in pl.bn:          # BatchNorm half: time the second backward pass (BN + conv + LN backward)
+                b = pl.bn[2]
+                coef = torch.zeros(3 * c["conv_nChan"], device=dev)
+                call = lambda: L.check(lib, lib.mmx_conv_half_bn_bwd2(C.byref(d), C.byref(tw), C.byref(tg), b["bn"].data_ptr(), coef.data_ptr(),
+                                                                      pl.acts[2].data_ptr(), b["z"].data_ptr(), pl.dact[0].data_ptr(),
+                                                                      b["gd"].data_ptr(), pl.dact[1].data_ptr(), st), "mmx_conv_half_bn_bwd2")
+            else:
+                call = lambda: L.check(lib, lib.mmx_conv_half_bwd(C.byref(d), C.byref(tw), C.byref(tg), pl.acts[2].data_ptr(), pl.dact[0].data_ptr(),
+                                                                  pl.dact[1].data_ptr(), st), "mmx_conv_half_bwd")
             tile = c["conv_nChan"] * c["in_nTP"] * c["dimPosEmb"] * 4
             kname = "conv_half_bwd (one ConvMixerBlock half backward, forward recomputed in-kernel)"
             kt, kp = mb.conv1.kernel

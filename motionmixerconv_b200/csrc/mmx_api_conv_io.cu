@@ -27,7 +27,7 @@ int plan_enc_fwd(const MmxEncoderDesc* d, EncDims* out, size_t* smem, int* grid)
     EncDims e;
     e.B = d->B; e.T = d->T; e.D = d->D; e.E = d->E; e.C = d->C; e.Hn = d->n_harmonic > 0 ? d->n_harmonic : 0;
     e.K = e.Hn > 0 ? 2 * e.Hn * e.D : e.D;
-    e.KC = e.Hn > 0 ? 64 : imin(round_up(e.D, 4), 128);
+    e.KC = e.Hn > 0 ? env_int("MMX_ENC_KC", 256) : imin(round_up(e.D, 4), 128);
     const int rows = e.B * e.T, n_ct = (e.E + 3) / 4;
     int R = 64;
     while (R > 4 && ((R + 3) / 4) * n_ct > kThreads) R /= 2;
@@ -58,7 +58,9 @@ int plan_head(const MmxConvHeadDesc* d, bool bwd, ConvHeadDims* out, size_t* sme
     ConvHeadDims h; h.B = d->B; h.C = d->C; h.T = d->T; h.To = d->To; h.E = d->E; h.D = d->D;
     const int two_cta_budget = (di.max_smem + 1024) / 2 - 2048;
     const int forced = env_int(bwd ? "MMX_CHEAD_S_BWD" : "MMX_CHEAD_S_FWD", 0);
-    const int S0 = forced > 0 ? forced : imax(1, 8192 / (imax(d->C * d->T, d->To) * d->E));
+    int S0 = imax(1, 8192 / (imax(d->C * d->T, d->To) * d->E));
+    S0 = imax(1, imin(S0, (d->B + 2 * di.sms - 1) / (2 * di.sms)));
+    if (forced > 0) S0 = forced;
     for (int pass = 0; pass < 2; ++pass) {
         const int budget = pass == 0 ? two_cta_budget : di.max_smem;
         for (int S = S0; S >= 1; --S) {
@@ -115,7 +117,7 @@ extern "C" int mmx_pose_encoder_bwd(const MmxEncoderDesc* d, const MmxEncoderPar
     }
     if (Hn == 0) return mmx_linear_bwd(rows, d->D, d->E, x, w->w, dm_ws, grads->w, grads->b, dx, stream);
     EncBwd2Args a;
-    a.d.B = d->B; a.d.T = d->T; a.d.D = d->D; a.d.E = d->E; a.d.Hn = Hn; a.d.R = 32; a.d.need_dx = dx != nullptr;
+    a.d.B = d->B; a.d.T = d->T; a.d.D = d->D; a.d.E = d->E; a.d.Hn = Hn; a.d.R = env_int("MMX_ENC_BWD_R", 128); a.d.need_dx = dx != nullptr;
     int HC = 32;
     while (HC > 2 && (HC > Hn || ((d->E + 3) / 4) * (2 * HC / 4) > kThreads)) HC /= 2;
     if (((d->E + 3) / 4) * (2 * HC / 4) > kThreads) return fail(MMX_E_UNSUPPORTED, "mmx_pose_encoder_bwd: dimPosEmb %d too large", d->E);

@@ -39,7 +39,10 @@ static inline int plan_conv_half(const MmxConvHalfDesc* d, bool bwd, ConvDims* o
     m.site = d->site; m.bn_mode = 0;
     const int two_cta_budget = (di.max_smem + 1024) / 2 - 2048;
     const int forced = env_int(bwd ? "MMX_CONV_S_BWD" : "MMX_CONV_S_FWD", 0);
-    const int S0 = forced > 0 ? forced : imax(1, kConvTileElems / (d->C * d->T * d->E));
+    // about kConvTileElems activations per tile, but never fewer tiles than ~2 per SM when the batch is small
+    int S0 = imax(1, kConvTileElems / (d->C * d->T * d->E));
+    S0 = imax(1, imin(S0, (d->B + 2 * di.sms - 1) / (2 * di.sms)));
+    if (forced > 0) S0 = forced;
     for (int in_smem = 1; in_smem >= 0; --in_smem) {
         m.x_in_smem = in_smem;
         if (!bwd && !in_smem) break;
