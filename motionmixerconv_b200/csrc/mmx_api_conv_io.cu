@@ -27,7 +27,13 @@ int plan_enc_fwd(const MmxEncoderDesc* d, EncDims* out, size_t* smem, int* grid)
     EncDims e;
     e.B = d->B; e.T = d->T; e.D = d->D; e.E = d->E; e.C = d->C; e.Hn = d->n_harmonic > 0 ? d->n_harmonic : 0;
     e.K = e.Hn > 0 ? 2 * e.Hn * e.D : e.D;
-    e.KC = e.Hn > 0 ? env_int("MMX_ENC_KC", 256) : imin(round_up(e.D, 4), 128);
+    if (e.Hn > 0) {       // a chunk = DC input dimensions: their sin and cos columns (2*DC*Hn embedding columns)
+        e.DC = imax(1, imin(e.D, env_int("MMX_ENC_KC", 256) / (2 * e.Hn)));
+        e.KC = round_up(2 * e.DC * e.Hn, 4);
+    } else {
+        e.DC = 0;
+        e.KC = imin(round_up(e.D, 4), 128);
+    }
     const int rows = e.B * e.T, n_ct = (e.E + 3) / 4;
     int R = 64;
     while (R > 4 && ((R + 3) / 4) * n_ct > kThreads) R /= 2;

@@ -15,6 +15,110 @@ MMX_D float mul_rn(float a, float b) { volatile float p = a * b; return p; }
 MMX_D float mul_rn(float a, float b) { return __fmul_rn(a, b); }   // ONE fp32 multiply, never contracted
 #endif
 
+
+// ------------------------------------------------------------------------------------------
+// Harmonic phases by exact angle doubling.
+// frequencies[h] = omega0 * 2^h (positional_encoder.py:54-57), so the fp32 argument of harmonic h is
+// a_h = fl32(x*f_h) = fl32(x*f_0) * 2^h EXACTLY (scaling by a power of two commutes with rounding).  Instead of one
+// Payne-Hanek reduction per (x, h) -- arguments reach 1e17 -- the phase frac(a_0 / 2pi) is formed ONCE as a 128-bit
+// fixed-point fraction (24-bit mantissa x 128 bits of 1/2pi) and harmonic h is a left shift by h bits.  sin/cos are then
+// evaluated on a float-float reduced argument in [-pi, pi) (fast path of sincosf), matching sinf(a_h)/cosf(a_h) of the
+// exact fp32 argument to ~2 ulp.  Used only when the frequency table really is f_0 * 2^h (checked on the device).
+// ------------------------------------------------------------------------------------------
+struct Phase128 { uint32_t w0, w1, w2, w3; };   // w0 most significant
+
+#if defined(MMX_HOST_EMU)
+static const uint32_t kInv2PiBits[13] =
+#else
+static __device__ __constant__ uint32_t kInv2PiBits[13] =
+#endif
+    {0u, 0u, 0u, 0u, 0x28be60dbu, 0x9391054au, 0x7f09d5f4u, 0x7d4d3770u, 0x36d8a566u, 0x4f10e410u, 0x7f9458eau, 0xf7aef158u, 0x6dc91b8eu};
+
+MMX_D uint32_t f2u(float f) {
+#if defined(MMX_HOST_EMU)
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#else
+    return __float_as_uint(f);
+#endif
+}
+
+// phase of |a|; returns false when a is zero / denormal / tiny / non-finite (caller evaluates sinf / cosf directly)
+MMX_D bool phase_init(float a, Phase128* ph, bool* neg) {
+    const uint32_t bits = f2u(a);
+    const int ex = (int)((bits >> 23) & 0xffu);
+    *neg = (bits >> 31) != 0u;
+    if (ex < 22 || ex == 255) return false;
+    const uint32_t m = (bits & 0x7fffffu) | 0x800000u;   // |a| = m * 2^(ex-150)
+    const int sh = ex - 22;                              // bits of (1/2pi * 2^-128) shifted out as integer part: 128 + (ex-150)
+    const int wo = sh >> 5, bo = sh & 31;
+    uint32_t k[4];
+    MMX_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t hi = kInv2PiBits[wo + i], lo = kInv2PiBits[wo + i + 1];
+        k[i] = bo ? (hi << bo) | (lo >> (32 - bo)) : hi;
+    }
+    uint64_t t = (uint64_t)m * k[3];
+    ph->w3 = (uint32_t)t; t = (uint64_t)m * k[2] + (t >> 32);
+    ph->w2 = (uint32_t)t; t = (uint64_t)m * k[1] + (t >> 32);
+    ph->w1 = (uint32_t)t; t = (uint64_t)m * k[0] + (t >> 32);
+    ph->w0 = (uint32_t)t;
+    return true;
+}
+MMX_D void phase_shl(Phase128* p, int n) {   // multiply the angle by 2^n (0 <= n < 128)
+    uint32_t w[8] = {p->w0, p->w1, p->w2, p->w3, 0u, 0u, 0u, 0u};
+    const int wo = n >> 5, bo = n & 31;
+    uint32_t r[4];
+    MMX_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        uint32_t hi = 0u, lo = 0u;
+        MMX_UNROLL
+        for (int j = 0; j < 4; ++j) { if (wo == j) { hi = w[i + j]; lo = w[i + j + 1]; } }
+        r[i] = bo ? (hi << bo) | (lo >> (32 - bo)) : hi;
+    }
+    p->w0 = r[0]; p->w1 = r[1]; p->w2 = r[2]; p->w3 = r[3];
+}
+MMX_D void phase_double(Phase128* p) {
+    p->w0 = (p->w0 << 1) | (p->w1 >> 31); p->w1 = (p->w1 << 1) | (p->w2 >> 31);
+    p->w2 = (p->w2 << 1) | (p->w3 >> 31); p->w3 <<= 1;
+}
+MMX_D void phase_sincos(const Phase128& p, bool neg, float* s, float* c) {
+    const float phi_hi = (float)(int32_t)(p.w0 & 0xffffff00u) * 2.3283064365386963e-10f;              // * 2^-32, exact
+    const float phi_lo = (float)(((p.w0 & 0xffu) << 16) | (p.w1 >> 16)) * 1.3877787807814457e-17f;    // * 2^-56, exact
+    const float C_HI = 6.2831854820251465f, C_LO = -1.7484556000744883e-07f;                          // 2pi = C_HI + C_LO
+    const float r_hi = phi_hi * C_HI;
+    const float r_lo = fmaf(phi_hi, C_HI, -r_hi) + fmaf(phi_hi, C_LO, phi_lo * C_HI);
+    const float s0 = sinf(r_hi), c0 = cosf(r_hi);
+    const float sv = fmaf(r_lo, c0, s0);
+    *s = neg ? -sv : sv;
+    *c = fmaf(-r_lo, s0, c0);
+}
+
+// sin / cos of fl32(x * freq[h]) for h = h0 .. h0+n-1 of one input value; out_s / out_c are strided by 1
+MMX_D void harmonics(float x, const float* freq, bool pow2, int h0, int n, float* out_s, float* out_c) {
+    Phase128 ph;
+    bool neg;
+    if (pow2 && phase_init(mul_rn(x, freq[0]), &ph, &neg)) {
+        phase_shl(&ph, h0);
+        for (int i = 0; i < n; ++i) {
+            phase_sincos(ph, neg, out_s + i, out_c + i);
+            phase_double(&ph);
+        }
+    } else {
+        for (int i = 0; i < n; ++i) {
+            const float arg = mul_rn(x, freq[h0 + i]);
+            out_s[i] = sinf(arg); out_c[i] = cosf(arg);
+        }
+    }
+}
+
+// 1 when freq[h] == freq[0] * 2^h for every h < Hn <= 64 (exact), else 0
+MMX_D int freq_is_pow2_ladder(const float* freq, int Hn) {
+    if (Hn > 64 || !(freq[0] > 0.0f)) return 0;
+    for (int h = 1; h < Hn; ++h)
+        if (freq[h] != ldexpf(freq[0], h)) return 0;
+    return 1;
+}
+
 // ==========================================================================================
 // "once"-mode tail:  y = x + SE(x)   (or 2x without SE)        conv_mixer_model.py:287-292
 // ==========================================================================================
@@ -165,17 +269,18 @@ struct EncDims {
     int B, T, D, E, C, Hn;
     int K;        // embedding width: Hn > 0 ? 2*Hn*D : D
     int KC;       // embedding columns per chunk (multiple of 4)
+    int DC;       // harmonic embedding: input dimensions per chunk (a chunk = their sin AND cos columns, KC >= 2*DC*Hn)
     int R;        // frames (rows of x) per CTA tile
 };
 struct EncW { float *freq, *w, *b, *wc, *bc; };   // frequencies[Hn], embed_mlp.{weight[E,K],bias[E]}, channelUpscaling.{weight[C,1],bias[C]}
-struct EncSmem { int PKC, PE, PD, x, emb, w, m, b, wc, bc, freq, total; };
+struct EncSmem { int PKC, PE, PD, x, emb, w, m, b, wc, bc, freq, flag, total; };
 MMX_HD EncSmem enc_smem(const EncDims& d) {
     EncSmem L;
     L.PKC = pitch_of(d.KC); L.PE = pitch_of(d.E); L.PD = round_up(d.D, 4);
     int o = 0;
     auto take = [&](int n) { int r = o; o += round_up(n, 4); return r; };
     L.x = take(d.R * L.PD); L.emb = take(d.R * L.PKC); L.w = take(d.E * L.PKC); L.m = take(d.R * L.PE);
-    L.b = take(d.E); L.wc = take(8); L.bc = take(8); L.freq = take(imax(d.Hn, 1));
+    L.b = take(d.E); L.wc = take(8); L.bc = take(8); L.freq = take(imax(d.Hn, 1)); L.flag = take(4);
     L.total = o;
     return L;
 }
@@ -200,12 +305,14 @@ MMX_D void enc_fwd_body(Exec& ex, const EncFwdArgs& a) {
     float* sm = ex.smem;
     const int nthr = ex.nthr, D = d.D, E = d.E, C = d.C, T = d.T, K = d.K, KC = d.KC, R = d.R, PKC = L.PKC, PE = L.PE;
     const int rows = d.B * T;
-    const int nchunks = (K + KC - 1) / KC;
+    const int Hn = d.Hn, DC = d.DC;
+    const int nchunks = Hn > 0 ? (D + DC - 1) / DC : (K + KC - 1) / KC;
     PerThread<EncFwdRegs> regs(ex);
     ex.phase([&](int tid) {
         copy_vec(tid, nthr, sm + L.b, a.w.b, E);
         for (int i = tid; i < 8; i += nthr) { sm[L.wc + i] = i < C ? a.w.wc[i] : 0.0f; sm[L.bc + i] = i < C ? a.w.bc[i] : 0.0f; }
-        if (d.Hn > 0) copy_vec(tid, nthr, sm + L.freq, a.w.freq, d.Hn);
+        if (Hn > 0) copy_vec(tid, nthr, sm + L.freq, a.w.freq, Hn);
+        if (tid == 0) sm[L.flag] = Hn > 0 ? (float)freq_is_pow2_ladder(a.w.freq, Hn) : 0.0f;
     });
     const int ntiles = (rows + R - 1) / R;
     for (int tile = ex.bid; tile < ntiles; tile += ex.nblk) {
@@ -226,15 +333,40 @@ MMX_D void enc_fwd_body(Exec& ex, const EncFwdArgs& a) {
                 for (int j = 0; j < 4; ++j) rg.acc[i][j] = 0.0f;
         });
         for (int ch = 0; ch < nchunks; ++ch) {
-            const int k0 = ch * KC, kc = imin(KC, K - k0), kc4 = (kc + 3) >> 2;
+            // chunk geometry.  Plain input: columns [k0, k0+kc) of x.  Harmonic: dims [d0, d0+dcv): their dcv*Hn sin columns
+            // (global column dd*Hn+h) followed by their dcv*Hn cos columns (global column Hn*D + dd*Hn+h)
+            const int d0 = ch * DC, dcv = Hn > 0 ? imin(DC, D - d0) : 0, half = dcv * Hn;
+            const int k0 = ch * KC, kc = Hn > 0 ? 2 * half : imin(KC, K - k0), kc4 = (kc + 3) >> 2;
             ex.phase([&](int tid) {
-                for (int i = tid; i < nr * 4 * kc4; i += nthr) {
-                    const int r = i / (4 * kc4), c = i - r * 4 * kc4;
-                    sm[L.emb + r * PKC + c] = c < kc ? enc_embed(sm + L.x + r * L.PD, sm + L.freq, D, d.Hn, k0 + c) : 0.0f;
-                }
-                for (int i = tid; i < E * 4 * kc4; i += nthr) {
-                    const int e = i / (4 * kc4), c = i - e * 4 * kc4;
-                    sm[L.w + e * PKC + c] = c < kc ? a.w.w[(size_t)e * K + k0 + c] : 0.0f;
+                if (Hn > 0) {
+                    const bool pow2 = sm[L.flag] != 0.0f;
+                    const int nseg = (Hn + 7) >> 3;
+                    for (int i = tid; i < nr * dcv * nseg; i += nthr) {
+                        const int hs = i % nseg, rd = i / nseg, dd = rd % dcv, r = rd / dcv;
+                        const int h0 = 8 * hs, n = imin(8, Hn - h0);
+                        float sv[8], cv[8];
+                        harmonics(sm[L.x + r * L.PD + d0 + dd], sm + L.freq, pow2, h0, n, sv, cv);
+                        float* es = sm + L.emb + r * PKC + dd * Hn + h0;
+                        for (int j = 0; j < n; ++j) { es[j] = sv[j]; es[half + j] = cv[j]; }
+                    }
+                    for (int i = tid; i < nr * (4 * kc4 - kc); i += nthr) {
+                        const int r = i / (4 * kc4 - kc), c = kc + (i - r * (4 * kc4 - kc));
+                        sm[L.emb + r * PKC + c] = 0.0f;
+                    }
+                    for (int i = tid; i < E * 4 * kc4; i += nthr) {
+                        const int e = i / (4 * kc4), c = i - e * 4 * kc4;
+                        const int col = c < half ? d0 * Hn + c : Hn * D + d0 * Hn + (c - half);
+                        sm[L.w + e * PKC + c] = c < kc ? a.w.w[(size_t)e * K + col] : 0.0f;
+                    }
+                } else {
+                    for (int i = tid; i < nr * 4 * kc4; i += nthr) {
+                        const int r = i / (4 * kc4), c = i - r * 4 * kc4;
+                        sm[L.emb + r * PKC + c] = c < kc ? sm[L.x + r * L.PD + k0 + c] : 0.0f;
+                    }
+                    for (int i = tid; i < E * 4 * kc4; i += nthr) {
+                        const int e = i / (4 * kc4), c = i - e * 4 * kc4;
+                        sm[L.w + e * PKC + c] = c < kc ? a.w.w[(size_t)e * K + k0 + c] : 0.0f;
+                    }
                 }
             });
             ex.phase([&](int tid) {
@@ -375,13 +507,13 @@ MMX_D void enc_bwd1_body(Exec& ex, const EncBwd1Args& a) {
 //     dx[r][dd]  += sum_h f[h] (cos(a) demb_sin - sin(a) demb_cos),   demb = dm W[:, cols]
 // ------------------------------------------------------------------------------------------
 struct EncBwd2Dims { int B, T, D, E, Hn, HC, R, need_dx; };
-struct EncBwd2Smem { int PE, P2, dm, emb, w, cont, x, freq, total; };
+struct EncBwd2Smem { int PE, P2, dm, emb, w, cont, x, freq, flag, total; };
 MMX_HD EncBwd2Smem enc_bwd2_smem(const EncBwd2Dims& d) {
     EncBwd2Smem L; L.PE = pitch_of(d.E); L.P2 = pitch_of(2 * d.HC);
     int o = 0;
     auto take = [&](int n) { int r = o; o += round_up(n, 4); return r; };
     L.dm = take(d.R * L.PE); L.emb = take(d.R * L.P2); L.w = take(d.E * L.P2); L.cont = take(d.R * L.P2);
-    L.x = take(d.R); L.freq = take(d.HC);
+    L.x = take(d.R); L.freq = take(d.Hn); L.flag = take(4);
     L.total = o;
     return L;
 }
@@ -408,7 +540,8 @@ MMX_D void enc_bwd2_body(Exec& ex, const EncBwd2Args& a) {
                 else if (c < 2 * HC) { if (c - HC < hc) v = a.w[(size_t)e * K + col_c + c - HC]; }
                 sm[L.w + i] = v;
             }
-            for (int i = tid; i < HC; i += nthr) sm[L.freq + i] = i < hc ? a.freq[h0 + i] : 0.0f;
+            for (int i = tid; i < Hn; i += nthr) sm[L.freq + i] = a.freq[i];
+            if (tid == 0) sm[L.flag] = (float)freq_is_pow2_ladder(a.freq, Hn);
             EncBwd2Regs& rg = regs[tid];
             MMX_UNROLL
             for (int i = 0; i < 4; ++i)
@@ -419,14 +552,17 @@ MMX_D void enc_bwd2_body(Exec& ex, const EncBwd2Args& a) {
             const int nr = imin(R, rows - row0);
             ex.phase([&](int tid) {
                 load_tile(tid, nthr, sm + L.dm, a.dm + (size_t)row0 * E, nr, E, PE);
-                for (int i = tid; i < nr * HC; i += nthr) {
-                    const int r = i / HC, h = i - r * HC;
-                    float sv = 0.0f, cv = 0.0f;
-                    if (h < hc) {
-                        const float arg = mul_rn(a.x[(size_t)(row0 + r) * D + dd], sm[L.freq + h]);
-                        sv = sinf(arg); cv = cosf(arg);
+                const bool pow2 = sm[L.flag] != 0.0f;
+                const int nsub = (HC + 7) >> 3;
+                for (int i = tid; i < nr * nsub; i += nthr) {
+                    const int r = i / nsub, sub = i - r * nsub;
+                    const int hh = 8 * sub, n = imax(0, imin(8, hc - hh));      // harmonics h0+hh .. of this CTA's segment
+                    float sv[8], cv[8];
+                    if (n > 0) harmonics(a.x[(size_t)(row0 + r) * D + dd], sm + L.freq, pow2, h0 + hh, n, sv, cv);
+                    for (int j = 0; j < imin(8, HC - hh); ++j) {
+                        sm[L.emb + r * P2 + hh + j] = j < n ? sv[j] : 0.0f;
+                        sm[L.emb + r * P2 + HC + hh + j] = j < n ? cv[j] : 0.0f;
                     }
-                    sm[L.emb + r * P2 + h] = sv; sm[L.emb + r * P2 + HC + h] = cv;
                 }
                 for (int i = tid; i < nr * (P2 - 2 * HC); i += nthr) {
                     const int r = i / (P2 - 2 * HC), c = 2 * HC + (i - r * (P2 - 2 * HC));
@@ -438,8 +574,8 @@ MMX_D void enc_bwd2_body(Exec& ex, const EncBwd2Args& a) {
                 if (d.need_dx)
                     gemm_nn<4>(tid, nthr, sm + L.dm, PE, sm + L.w, P2, nr, 2 * HC, E, [&](int m, int n, float v) {
                         // d sin(a)/da = cos(a), d cos(a)/da = -sin(a); da/dx = f
-                        const float c = n < HC ? v * sm[L.emb + m * P2 + n + HC] * sm[L.freq + n]
-                                               : -v * sm[L.emb + m * P2 + n - HC] * sm[L.freq + n - HC];
+                        const float fr = sm[L.freq + imin(h0 + (n < HC ? n : n - HC), Hn - 1)];
+                        const float c = n < HC ? v * sm[L.emb + m * P2 + n + HC] * fr : -v * sm[L.emb + m * P2 + n - HC] * fr;
                         sm[L.cont + m * P2 + n] = c;
                     });
             });

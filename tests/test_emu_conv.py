@@ -77,3 +77,33 @@ def test_emulated_multi_tile_and_streamed_inputs(case, B, S, xg, monkeypatch):
     for k in O.trainable_keys(g.params):
         check_close("grad " + k, grads[k], g32[k], g64[k], rtol=TOL, atol=floor * ZERO_GRAD_SLACK.get(k, 1))
     check_close("dx", dx, dx32, dx64, rtol=TOL, atol=1e-6 * float(np.abs(dx32).max()))
+
+
+def test_emulated_harmonic_embedding_exact_angle_doubling():
+    """The harmonic encoder evaluates sin/cos(fl32(x*f_h)), f_h = omega0*2^h up to 9e17, from ONE 128-bit phase per input
+    value and bit shifts (mmx_conv_io.cuh).  With an identity embed_mlp the kernel returns the embedding itself: it must
+    match sin/cos of the exact fp32 argument (positional_encoder.py:86-89) for every harmonic, and the generic path
+    (frequency table that is not a power-of-two ladder) must agree."""
+    import ctypes as C
+    from motionmixerconv_b200 import _lib as L
+    rng = np.random.default_rng(0)
+    Hn, D, T = 64, 1, 8
+    xs = np.concatenate([rng.standard_normal(40) * 0.4, [0.0, 1e-30, -3.7e-12, 7.25, -1234.5, 2.0 ** -20, 0.5, -0.5]]).astype(np.float32)
+    B = len(xs) // T
+    x = H.f32(xs[:B * T].reshape(B, T, D))
+    K = 2 * Hn * D
+    for ladder in (True, False):
+        freq = (np.float32(0.1) * (2.0 ** np.arange(Hn))).astype(np.float32)
+        if not ladder:
+            freq = (freq * np.float32(1.0 + 2.0 ** -20)).astype(np.float32)
+            freq[5] = np.float32(3.3)                              # breaks the ladder: generic sinf/cosf path
+        w, b = H.f32(np.eye(K)), H.f32(np.zeros(K))
+        wc, bc = H.f32(np.ones((1, 1))), H.f32(np.zeros(1))
+        tab = L.MmxEncoderParams()
+        tab.freq, tab.w, tab.b, tab.wc, tab.bc = H.ptr(freq), H.ptr(w), H.ptr(b), H.ptr(wc), H.ptr(bc)
+        m = np.empty((B * T, K), np.float32)
+        y = np.empty((B, 1, T, K), np.float32)
+        H.call("mmx_pose_encoder_fwd", C.byref(L.MmxEncoderDesc(B, T, D, K, 1, Hn)), C.byref(tab), H.ptr(x), H.ptr(m), H.ptr(y), None)
+        arg = (x.reshape(-1, 1) * freq[None, :]).astype(np.float32).astype(np.float64)   # ONE fp32 multiply, then exact
+        want = np.concatenate([np.sin(arg), np.cos(arg)], axis=1)
+        assert np.abs(m - want).max() <= 4e-7, (ladder, np.abs(m - want).max())
