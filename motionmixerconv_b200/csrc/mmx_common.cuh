@@ -463,6 +463,40 @@ MMX_D void gemm_tn_acc4x4(float (&acc)[4][4], int tile, int n_nt, const float* A
     }
 }
 
+// store an accumulator tile into a row-major SHARED staging matrix [M][ld] (then one coalesced RED pass flushes it:
+// lane-contiguous addresses instead of 16-byte-strided ones)
+MMX_D void stage_acc4x4(const float (&acc)[4][4], int tile, int n_nt, float* S, int ld, int M, int N) {
+    const int mt = tile / n_nt, nt = tile - mt * n_nt;
+    MMX_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        const int m = 4 * mt + i;
+        if (m < M) {
+            MMX_UNROLL
+            for (int j = 0; j < 4; ++j) {
+                const int n = 4 * nt + j;
+                if (n < N) S[m * ld + n] = acc[i][j];
+            }
+        }
+    }
+}
+
+// add an accumulator tile into a row-major SHARED matrix [M][ld] with shared atomics (combines the K-split slices of a CTA
+// before ONE global RED per element: many threads RED-ing the same few addresses serialise in L2)
+MMX_D void smem_add_acc4x4(const float (&acc)[4][4], int tile, int n_nt, float* S, int ld, int M, int N) {
+    const int mt = tile / n_nt, nt = tile - mt * n_nt;
+    MMX_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        const int m = 4 * mt + i;
+        if (m < M) {
+            MMX_UNROLL
+            for (int j = 0; j < 4; ++j) {
+                const int n = 4 * nt + j;
+                if (n < N) smem_add(S + m * ld + n, acc[i][j]);
+            }
+        }
+    }
+}
+
 // flush an accumulator tile into a row-major global gradient [M][ldg] with RED.ADD
 MMX_D void flush_acc4x4(const float (&acc)[4][4], int tile, int n_nt, float* G, int ldg, int M, int N) {
     const int mt = tile / n_nt, nt = tile - mt * n_nt;

@@ -619,7 +619,7 @@ struct ConvHeadDims { int B, C, T, To, E, D, S; };
 struct ConvHeadW { float *ln_g, *ln_b, *wt, *bt, *wp, *bp, *wf, *bf; };
 struct ConvHeadSmem {
     int PE, PD, R, ln_g, ln_b, wt, bt, wp, wf, bf, part, part2, mean, rstd, bY, bQ, bR, bG, bO;
-    int a_lng, a_lnb, a_bf, a_bt, a_wp, a_bp, total;
+    int a_lng, a_lnb, a_bf, a_bt, a_wp, a_bp, a_wt, total;
 };
 MMX_HD ConvHeadSmem conv_head_smem(const ConvHeadDims& d, bool bwd) {
     ConvHeadSmem L; L.PE = pitch_of(d.E); L.PD = pitch_of(d.D); L.R = d.S * d.C * d.T;
@@ -636,7 +636,8 @@ MMX_HD ConvHeadSmem conv_head_smem(const ConvHeadDims& d, bool bwd) {
         L.bR = take(d.S * d.To * L.PE);
         L.bO = take(d.S * d.To * L.PD);
         L.a_lng = take(d.E); L.a_lnb = take(d.E); L.a_bf = take(d.D); L.a_bt = take(d.To); L.a_wp = take(8); L.a_bp = take(4);
-    } else { L.bR = L.bO = L.a_lng = L.a_lnb = L.a_bf = L.a_bt = L.a_wp = L.a_bp = -1; }
+        L.a_wt = take(d.To * d.T);
+    } else { L.bR = L.bO = L.a_lng = L.a_lnb = L.a_bf = L.a_bt = L.a_wp = L.a_bp = L.a_wt = -1; }
     L.total = o;
     return L;
 }
@@ -735,7 +736,7 @@ MMX_D void conv_head_bwd_body(Exec& ex, const ConvHeadBwdArgs& a) {
         conv_head_stage(tid, nthr, sm, L, d, a.w);
         zero_vec(tid, nthr, sm + L.a_lng, E); zero_vec(tid, nthr, sm + L.a_lnb, E);
         zero_vec(tid, nthr, sm + L.a_bf, D); zero_vec(tid, nthr, sm + L.a_bt, To);
-        zero_vec(tid, nthr, sm + L.a_wp, 8); zero_vec(tid, nthr, sm + L.a_bp, 4);
+        zero_vec(tid, nthr, sm + L.a_wp, 8); zero_vec(tid, nthr, sm + L.a_bp, 4); zero_vec(tid, nthr, sm + L.a_wt, To * T);
         ConvHeadBwdRegs<WT>& rg = regs[tid];
         MMX_UNROLL
         for (int w = 0; w < WT; ++w)
@@ -889,12 +890,15 @@ MMX_D void conv_head_bwd_body(Exec& ex, const ConvHeadBwdArgs& a) {
             }
         }
         const int slice = tid / t_tiles, otile = tid - slice * t_tiles;
-        if (slice < n_slices) flush_acc4x4(rg.dWt, otile, t_nt, a.g.wt, T, To, T);
+        if (slice < n_slices) smem_add_acc4x4(rg.dWt, otile, t_nt, sm + L.a_wt, T, To, T);    // combine the CTA's K-split slices
         for (int e = tid; e < E; e += nthr) { red_add(a.g.ln_g + e, sm[L.a_lng + e]); red_add(a.g.ln_b + e, sm[L.a_lnb + e]); }
         for (int n = tid; n < D; n += nthr) red_add(a.g.bf + n, sm[L.a_bf + n]);
         for (int o = tid; o < To; o += nthr) red_add(a.g.bt + o, sm[L.a_bt + o]);
         for (int c = tid; c < C; c += nthr) red_add(a.g.wp + c, sm[L.a_wp + c] + sm[L.a_bp + 1]);
         if (tid == 0) red_add(a.g.bp, sm[L.a_bp]);
+    });
+    ex.phase([&](int tid) {
+        for (int i = tid; i < To * T; i += nthr) red_add(a.g.wt + i, sm[L.a_wt + i]);
     });
 }
 

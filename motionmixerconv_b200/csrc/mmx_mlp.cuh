@@ -122,16 +122,29 @@ MMX_D void load_tile(int tid, int nthr, float* dst, const float* src, int nr, in
             const int r = i / W4, q = i - r * W4;
             st4(dst + r * P + 4 * q, ld4(src + (size_t)r * W + 4 * q));
         }
+    } else if ((((uintptr_t)src) & 15) == 0) {
+        // rows are not 16-byte multiples, but the tile is one contiguous, aligned run: stream it as float4 and scatter
+        const int total = nr * W, Q = total >> 2;
+        for (int i = tid; i < Q; i += nthr) {
+            const f4 v = ld4(src + 4 * i);
+            int r = (4 * i) / W, c = 4 * i - r * W;
+            dst[r * P + c] = v.x; if (++c == W) { c = 0; ++r; }
+            dst[r * P + c] = v.y; if (++c == W) { c = 0; ++r; }
+            dst[r * P + c] = v.z; if (++c == W) { c = 0; ++r; }
+            dst[r * P + c] = v.w;
+        }
+        for (int i = 4 * Q + tid; i < total; i += nthr) { const int r = i / W, c = i - r * W; dst[r * P + c] = src[i]; }
+    } else {
+        for (int i = tid; i < nr * W; i += nthr) {
+            const int r = i / W, c = i - r * W;
+            dst[r * P + c] = src[(size_t)r * W + c];
+        }
+    }
+    if (P > W)
         for (int i = tid; i < nr * (P - W); i += nthr) {
             const int r = i / (P - W), c = W + (i - r * (P - W));
             dst[r * P + c] = 0.0f;
         }
-    } else {
-        for (int i = tid; i < nr * P; i += nthr) {
-            const int r = i / P, c = i - r * P;
-            dst[i] = c < W ? src[(size_t)r * W + c] : 0.0f;
-        }
-    }
 }
 MMX_D void store_tile(int tid, int nthr, float* dst, const float* src, int nr, int W, int P) {
     if ((W & 3) == 0) {
@@ -140,6 +153,18 @@ MMX_D void store_tile(int tid, int nthr, float* dst, const float* src, int nr, i
             const int r = i / W4, q = i - r * W4;
             st4(dst + (size_t)r * W + 4 * q, ld4(src + r * P + 4 * q));
         }
+    } else if ((((uintptr_t)dst) & 15) == 0) {
+        const int total = nr * W, Q = total >> 2;
+        for (int i = tid; i < Q; i += nthr) {
+            int r = (4 * i) / W, c = 4 * i - r * W;
+            f4 v;
+            v.x = src[r * P + c]; if (++c == W) { c = 0; ++r; }
+            v.y = src[r * P + c]; if (++c == W) { c = 0; ++r; }
+            v.z = src[r * P + c]; if (++c == W) { c = 0; ++r; }
+            v.w = src[r * P + c];
+            st4(dst + 4 * i, v);
+        }
+        for (int i = 4 * Q + tid; i < total; i += nthr) { const int r = i / W, c = i - r * W; dst[i] = src[r * P + c]; }
     } else {
         for (int i = tid; i < nr * W; i += nthr) {
             const int r = i / W, c = i - r * W;
@@ -834,6 +859,7 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
     }
 
     // ---------------- flush the CTA's gradient accumulators ----------------
+    ex.phase([&](int tid) { zero_vec(tid, nthr, sm + L.bD, 2 * T * tok); });
     ex.phase([&](int tid) {
         MlpBwdRegs<WT>& rg = regs[tid];
         if (persist) {
@@ -845,9 +871,9 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
             }
         }
         const int slice = tid / tk_tiles, otile = tid - slice * tk_tiles;
-        if (slice < n_slices) {
-            if (otile < w2_tiles) flush_acc4x4(rg.dW2, otile, w2_nt, a.g.tw2, tok, T, tok);
-            if (otile < w1_tiles) flush_acc4x4(rg.dW1, otile, w1_nt, a.g.tw1, T, tok, T);
+        if (slice < n_slices) {       // combine the CTA's K-split slices in shared memory (tiles bX / bD are idle now)
+            if (otile < w2_tiles) smem_add_acc4x4(rg.dW2, otile, w2_nt, sm + L.bD, tok, T, tok);
+            if (otile < w1_tiles) smem_add_acc4x4(rg.dW1, otile, w1_nt, sm + L.bD + T * tok, T, tok, T);
         }
         for (int k = tid; k < tok; k += nthr) red_add(a.g.tb1 + k, sm[L.a_tb1 + k]);
         for (int t = tid; t < T; t += nthr) red_add(a.g.tb2 + t, sm[L.a_tb2 + t]);
@@ -859,6 +885,9 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
         for (int c = tid; c < ch; c += nthr) red_add(a.g.cb1 + c, sm[L.a_cb1 + c]);
         if (d.use_se)
             for (int i = tid; i < T * rr; i += nthr) { red_add(a.g.se1 + i, sm[L.a_se1 + i]); red_add(a.g.se2 + i, sm[L.a_se2 + i]); }
+    });
+    ex.phase([&](int tid) {
+        for (int i = tid; i < T * tok; i += nthr) { red_add(a.g.tw2 + i, sm[L.bD + i]); red_add(a.g.tw1 + i, sm[L.bD + T * tok + i]); }
     });
 }
 
@@ -938,10 +967,14 @@ MMX_D void linear_bwd_body(Exec& ex, const LinearBwdArgs& a) {
             load_tile(tid, nthr, sm + L.dy, a.dy + (size_t)row0 * N, nr, N, L.PN);
         });
         ex.phase([&](int tid) {
-            for (int n = tid; n < N; n += nthr) {
-                float s = 0.0f;
-                for (int r = 0; r < nr; ++r) s += sm[L.dy + r * L.PN + n];
-                s_db[n] += s;
+            {
+                const int nsl = imax(1, nthr / N);
+                for (int it = tid; it < N * nsl; it += nthr) {
+                    const int sl = it / N, n = it - sl * N;
+                    float s = 0.0f;
+                    for (int r = sl; r < nr; r += nsl) s += sm[L.dy + r * L.PN + n];
+                    smem_add(s_db + n, s);
+                }
             }
             LinearBwdRegs<WT>& rg = regs[tid];
             if (persist) {
@@ -965,17 +998,25 @@ MMX_D void linear_bwd_body(Exec& ex, const LinearBwdArgs& a) {
             }
         });
     }
+    const bool staged = persist && N * K <= R * L.PK;     // dW fits the (now idle) x tile: coalesced flush through shared memory
     ex.phase([&](int tid) {
         LinearBwdRegs<WT>& rg = regs[tid];
         if (persist) {
             MMX_UNROLL
             for (int w = 0; w < WT; ++w) {
                 const int t = tid + w * nthr;
-                if (t < w_tiles) flush_acc4x4(rg.dW[w], t, w_nt, a.dw, K, N, K);
+                if (t < w_tiles) {
+                    if (staged) stage_acc4x4(rg.dW[w], t, w_nt, sm + L.x, K, N, K);
+                    else flush_acc4x4(rg.dW[w], t, w_nt, a.dw, K, N, K);
+                }
             }
         }
         for (int n = tid; n < N; n += nthr) red_add(a.db + n, s_db[n]);
     });
+    if (staged)
+        ex.phase([&](int tid) {
+            for (int i = tid; i < N * K; i += nthr) red_add(a.dw + i, sm[L.x + i]);
+        });
 }
 
 // ------------------------------------------------------------------------------------------
@@ -985,7 +1026,7 @@ MMX_D void linear_bwd_body(Exec& ex, const LinearBwdArgs& a) {
 struct MlpHeadDims { int B, T, To, H, D, S; };
 struct MlpHeadW { float *ln_g, *ln_b, *wt, *bt, *wf, *bf; };   // LN.{weight,bias}, conv_out.{weight[To,T,1],bias}, fc_out.{weight[D,H],bias}
 struct MlpHeadSmem {
-    int PH, PD, ln_g, ln_b, wt, bt, wf, bf, mean, rstd, bX, bP, bO, bZ, a_lng, a_lnb, a_bf, a_bt, total;
+    int PH, PD, ln_g, ln_b, wt, bt, wf, bf, mean, rstd, bX, bP, bO, bZ, a_lng, a_lnb, a_bf, a_bt, a_wt, total;
 };
 MMX_HD MlpHeadSmem mlp_head_smem(const MlpHeadDims& d, bool bwd) {
     MlpHeadSmem L; L.PH = pitch_of(d.H); L.PD = pitch_of(d.D);
@@ -999,8 +1040,8 @@ MMX_HD MlpHeadSmem mlp_head_smem(const MlpHeadDims& d, bool bwd) {
     if (bwd) {
         L.bO = take(d.S * d.To * L.PD);          // dOut tile
         L.bZ = take(d.S * d.T * L.PH);           // Z = LN(X), later dZ
-        L.a_lng = take(d.H); L.a_lnb = take(d.H); L.a_bf = take(d.D); L.a_bt = take(d.To);
-    } else { L.bO = L.bZ = L.a_lng = L.a_lnb = L.a_bf = L.a_bt = -1; }
+        L.a_lng = take(d.H); L.a_lnb = take(d.H); L.a_bf = take(d.D); L.a_bt = take(d.To); L.a_wt = take(d.To * d.T);
+    } else { L.bO = L.bZ = L.a_lng = L.a_lnb = L.a_bf = L.a_bt = L.a_wt = -1; }
     L.total = o;
     return L;
 }
@@ -1076,7 +1117,7 @@ MMX_D void mlp_head_bwd_body(Exec& ex, const MlpHeadBwdArgs& a) {
         copy_vec(tid, nthr, sm + L.wt, a.w.wt, To * T); copy_vec(tid, nthr, sm + L.bt, a.w.bt, To);
         stage_matrix(tid, nthr, sm + L.wf, a.w.wf, D, H, PH);
         zero_vec(tid, nthr, sm + L.a_lng, H); zero_vec(tid, nthr, sm + L.a_lnb, H);
-        zero_vec(tid, nthr, sm + L.a_bf, D); zero_vec(tid, nthr, sm + L.a_bt, To);
+        zero_vec(tid, nthr, sm + L.a_bf, D); zero_vec(tid, nthr, sm + L.a_bt, To); zero_vec(tid, nthr, sm + L.a_wt, To * T);
         MlpHeadBwdRegs<WT>& rg = regs[tid];
         MMX_UNROLL
         for (int w = 0; w < WT; ++w)
@@ -1126,10 +1167,14 @@ MMX_D void mlp_head_bwd_body(Exec& ex, const MlpHeadBwdArgs& a) {
         });
         // dbf, dWf[d][h] += sum_rows dOut[row][d] P[row][h]
         ex.phase([&](int tid) {
-            for (int n = tid; n < D; n += nthr) {
-                float s = 0.0f;
-                for (int r = 0; r < no; ++r) s += sm[L.bO + r * PD + n];
-                sm[L.a_bf + n] += s;
+            {
+                const int nsl = imax(1, nthr / D);            // row slices per column: all threads busy
+                for (int it = tid; it < D * nsl; it += nthr) {
+                    const int sl = it / D, n = it - sl * D;
+                    float s = 0.0f;
+                    for (int r = sl; r < no; r += nsl) s += sm[L.bO + r * PD + n];
+                    smem_add(sm + L.a_bf + n, s);
+                }
             }
             MlpHeadBwdRegs<WT>& rg = regs[tid];
             if (persist) {
@@ -1174,13 +1219,15 @@ MMX_D void mlp_head_bwd_body(Exec& ex, const MlpHeadBwdArgs& a) {
                     }
                 }
             }
-            for (int o = tid; o < To; o += nthr) {
+            for (int i = tid; i < no * 4; i += nthr) {       // dbt[o] = sum_{s,h} dP[(s,o)][h]: (row, quarter) partials
+                const int r = i >> 2, part = i & 3;
+                const float* row = sm + L.bP + r * PH;
                 float s = 0.0f;
-                for (int sq = 0; sq < ns; ++sq) {
-                    const float* row = sm + L.bP + (sq * To + o) * PH;
-                    for (int h = 0; h < H; ++h) s += row[h];
+                for (int h = 4 * part; h < H; h += 16) {
+                    const int n = imin(4, H - h);
+                    for (int k = 0; k < n; ++k) s += row[h + k];
                 }
-                sm[L.a_bt + o] += s;
+                smem_add(sm + L.a_bt + (r % To), s);
             }
         });
         ex.phase([&](int tid) {   // dZ[(s,t)][h] = sum_o Wt[o][t] dP[(s,o)][h]   -> bZ (Z is dead after dWt)
@@ -1201,13 +1248,15 @@ MMX_D void mlp_head_bwd_body(Exec& ex, const MlpHeadBwdArgs& a) {
             }
         });
         ex.phase([&](int tid) {   // LN backward: columns (dgamma, dbeta) and rows (dX -> bX in place)
-            for (int h = tid; h < H; h += nthr) {
+            const int nsl = imax(1, nthr / H);
+            for (int it = tid; it < H * nsl; it += nthr) {
+                const int sl = it / H, h = it - sl * H;
                 float sg = 0.0f, sb = 0.0f;
-                for (int r = 0; r < nr; ++r) {
+                for (int r = sl; r < nr; r += nsl) {
                     const float dn = sm[L.bZ + r * PH + h];
                     sg = fmaf(dn, (sm[L.bX + r * PH + h] - sm[L.mean + r]) * sm[L.rstd + r], sg); sb += dn;
                 }
-                sm[L.a_lng + h] += sg; sm[L.a_lnb + h] += sb;
+                smem_add(sm + L.a_lng + h, sg); smem_add(sm + L.a_lnb + h, sb);
             }
         });
         ex.phase([&](int tid) {
@@ -1229,20 +1278,29 @@ MMX_D void mlp_head_bwd_body(Exec& ex, const MlpHeadBwdArgs& a) {
         });
         ex.phase([&](int tid) { store_tile(tid, nthr, a.dx + (size_t)seq0 * T * H, sm + L.bX, nr, H, PH); });
     }
+    const bool staged = persist && D * H <= S * T * PH;    // dWf fits the (now idle) x tile: coalesced flush through shared memory
     ex.phase([&](int tid) {
         MlpHeadBwdRegs<WT>& rg = regs[tid];
         if (persist) {
             MMX_UNROLL
             for (int w = 0; w < WT; ++w) {
                 const int t = tid + w * nthr;
-                if (t < f_tiles) flush_acc4x4(rg.dWf[w], t, f_nt, a.g.wf, H, D, H);
+                if (t < f_tiles) {
+                    if (staged) stage_acc4x4(rg.dWf[w], t, f_nt, sm + L.bX, H, D, H);
+                    else flush_acc4x4(rg.dWf[w], t, f_nt, a.g.wf, H, D, H);
+                }
             }
         }
         const int slice = tid / t_tiles, otile = tid - slice * t_tiles;
-        if (slice < n_slices) flush_acc4x4(rg.dWt, otile, t_nt, a.g.wt, T, To, T);
+        if (slice < n_slices) smem_add_acc4x4(rg.dWt, otile, t_nt, sm + L.a_wt, T, To, T);    // combine the CTA's K-split slices
         for (int h = tid; h < H; h += nthr) { red_add(a.g.ln_g + h, sm[L.a_lng + h]); red_add(a.g.ln_b + h, sm[L.a_lnb + h]); }
         for (int n = tid; n < D; n += nthr) red_add(a.g.bf + n, sm[L.a_bf + n]);
         for (int o = tid; o < To; o += nthr) red_add(a.g.bt + o, sm[L.a_bt + o]);
+    });
+    ex.phase([&](int tid) {
+        for (int i = tid; i < To * T; i += nthr) red_add(a.g.wt + i, sm[L.a_wt + i]);
+        if (staged)
+            for (int i = tid; i < D * H; i += nthr) red_add(a.g.wf + i, sm[L.bX + i]);
     });
 }
 
