@@ -74,7 +74,7 @@ MMX_D void warp_lock(unsigned int* l, int lane) {
     (void)l; (void)lane;
 #else
     if (lane == 0) {
-        while (atomicCAS(l, 0u, 1u) != 0u) { __nanosleep(32); }
+        while (atomicCAS(l, 0u, 1u) != 0u) {}
         __threadfence_block();
     }
     __syncwarp();
@@ -219,12 +219,7 @@ float dropout_scale(const Dropout& d, uint32_t site, uint64_t elem) {
 // Two quads per Philox call (16 random bits per element): `pair` numbers consecutive row pairs of a [rows][W] site,
 // ks0 / ks1 are the keep-scales of quad `q` of the pair's first / second row.  Philox4x32-7 (Crush-resistant per
 // Salmon et al., SC'11): the masks only need to be uncorrelated, not cryptographic.
-#if defined(MMX_HOST_EMU)
-inline
-#else
-static __device__ __noinline__
-#endif
-void dropout_rowpair(const Dropout& d, uint32_t site, uint64_t pair, int q, int W4, float (&ks0)[4], float (&ks1)[4]) {
+MMX_D void dropout_rowpair(const Dropout& d, uint32_t site, uint64_t pair, int q, int W4, float (&ks0)[4], float (&ks1)[4]) {
     const uint64_t ctr = pair * (uint64_t)W4 + (uint64_t)q;
     uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = site ^ 0x5bd1e995u, c3 = d.step, k0 = d.seed_lo, k1 = d.seed_hi;
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

@@ -54,7 +54,7 @@ MMX_HD MlpWarpSmem mlp_warp_smem(const MlpDims& d, bool bwd, int nwarp) {
     L.tw1 = take(tok * L.TP); L.tb1 = take(tok); L.tw2t = take(tok * L.TP); L.tb2 = take(L.TP);
     L.se1 = take(rr * T); L.se2 = take(T * rr);
     L.v1 = take(ch * L.PH); L.v2 = take(H * L.PC);
-    if (bwd) { L.a_v1 = take(64 * kAccP); L.a_v2 = take(64 * kAccP); L.lock = take(4); }
+    if (bwd) { L.a_v1 = take(64 * kAccP); L.a_v2 = take(64 * kAccP); L.lock = take(4); }   // locks: dV1 pass 0/1, dV2 pass 0/1
     else L.a_v1 = L.a_v2 = L.lock = -1;
     L.warp0 = o;
     int w = 0;
@@ -213,7 +213,7 @@ MMX_D void warp_wgrad(float* accm, unsigned int* lock, const float* At, const fl
                 }
             }
         }
-        warp_lock(lock, lane);
+        warp_lock(lock + pass, lane);      // one lock per (matrix, column half): the two passes touch disjoint columns
         if (work) {
             MMX_UNROLL
             for (int i = 0; i < 8; ++i) {
@@ -227,7 +227,7 @@ MMX_D void warp_wgrad(float* accm, unsigned int* lock, const float* At, const fl
                 }
             }
         }
-        warp_unlock(lock, lane);
+        warp_unlock(lock + pass, lane);
     }
 }
 
@@ -761,7 +761,7 @@ MMX_D void mlp_block_bwd_warp_body(Exec& ex, const MlpBlockBwdArgs& a) {
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM
                 const bool live0 = (long long)grp * kSPW < d.B, live1 = (long long)grp * kSPW + 1 < d.B;
-                warp_wgrad<TC>(sm + L.a_v2, locks + 1, ws + L.tile[2], ws + L.tile[1], P, H, ch, lane, live0, live1);
+                warp_wgrad<TC>(sm + L.a_v2, locks + 2, ws + L.tile[2], ws + L.tile[1], P, H, ch, lane, live0, live1);
                 MMX_UNROLL
                 for (int t = 0; t < TC; ++t)
                     MMX_UNROLL

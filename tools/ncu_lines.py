@@ -31,7 +31,7 @@ hdr = rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 data, seen = [], set()
 for r in rows[2:]:
-    if len(r) < len(hdr) or r[idx["Address"]] in seen:
+    if len(r) < len(hdr) or r[idx["Address"]] in seen or r[idx["Address"]] == "Address":
         continue
     seen.add(r[idx["Address"]])
     data.append(r)
