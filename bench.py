@@ -284,8 +284,16 @@ def run_ours(args, w):
         peak, which = peaks()
         ach = alg / (t_k * 1e-3) / 1e9
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12     # fp32 FMA pipe: 148 SMs x 128 lanes x 2 flop x 1.965 GHz (nominal)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                ent = json.load(f).get(args.workload)
+            if ent:
+                traffic, traffic_src = ent["bytes"], ent["source"]
         roof = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "peak_source": which, "algorithmic_bytes_per_launch": alg, "kernel_ms": t_k, "traffic": None,
+                "peak_source": which, "algorithmic_bytes_per_launch": alg, "kernel_ms": t_k, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "fp32_tflops": flops / (t_k * 1e-3) / 1e12, "fp32_frac": flops / (t_k * 1e-3) / 1e12 / fp32_peak,
                 "note": "fp32 SIMT (1e-5 parity mode): the kernel is bound by the fp32 pipe / latency, not HBM — see DESIGN.md §4"}
 
