@@ -182,6 +182,17 @@ int mmx_conv_head_fwd(const MmxConvHeadDesc* d, const MmxConvHeadParams* w, cons
 int mmx_conv_head_bwd(const MmxConvHeadDesc* d, const MmxConvHeadParams* w, const MmxConvHeadParams* grads,
                       const float* y, const float* dout, float* dy, void* stream);
 
+/* ---------------- the callers either side of model(x) ---------------- */
+
+/* Step input (train_mixer_h36m.py:117-120,179): x = batch[:, :T, dim_used] * x_scale, gt = batch[:, T:T+To, dim_used] * gt_scale.
+ * batch: [B,Ttot,Dfull], dim_used: DEVICE int32 [D], x: [B,T,D], gt: [B,To,D]. */
+int mmx_window_split(const float* batch, int B, int Ttot, int Dfull, const int* dim_used, int D, int T, int To,
+                     float x_scale, float gt_scale, float* x, float* gt, void* stream);
+
+/* PCK histogram for auc_pck_metric (utils/utils_mixer.py:20-45): hist[k] += #joints with thresh[k-1] < ||pred-gt|| <= thresh[k]
+ * (k = 0: <= thresh[0]; k = n: > thresh[n-1]); PCK(thresh[k]) = cumsum(hist)[k] / n_joints.  hist: DEVICE int32 [n+1], accumulated. */
+int mmx_pck_hist(const float* pred, const float* gt, long long n_joints, const float* thresh, int n, int* hist, void* stream);
+
 /* ---------------- loss / optimiser ---------------- */
 
 /* MPJPE (utils_mixer.py:48-53): *loss_sum += sum_joints ||gt - pred||_2 (caller zeroes it; mean =

@@ -97,6 +97,9 @@ SIGNATURES = {
     "mmx_conv_head_fwd": (C.c_int, [C.POINTER(MmxConvHeadDesc), C.POINTER(MmxConvHeadParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_conv_head_bwd": (C.c_int, [C.POINTER(MmxConvHeadDesc), C.POINTER(MmxConvHeadParams), C.POINTER(MmxConvHeadParams),
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_window_split": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_pck_hist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mmx_mpjpe_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p]),
     "mmx_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "mmx_adam_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -513,3 +513,46 @@ class _ConvHead(torch.autograd.Function):
 
 def conv_head(y, ln_w, ln_b, wt, bt, wp, bp, wf, bf):
     return _ConvHead.apply(y, ln_w, ln_b, wt, bt, wp, bp, wf, bf)
+
+
+# ------------------------------------------------------------------------------------------------
+# the callers either side of model(x): step input (train_mixer_h36m.py:117-120,179), PCK / AUC (utils_mixer.py:20-45)
+# ------------------------------------------------------------------------------------------------
+def window_split(batch, dim_used, input_n, output_n, x_scale=1.0, gt_scale=1.0, out=None):
+    """``(batch[:, :input_n, dim_used] * x_scale, batch[:, input_n:input_n+output_n, dim_used] * gt_scale)`` in one pass over
+    the raw window.  ``dim_used``: int32 CUDA tensor (or anything convertible).  ``out``: optional preallocated (x, gt)."""
+    batch = _chk(batch, "batch")
+    if not isinstance(dim_used, torch.Tensor):
+        dim_used = torch.as_tensor(dim_used, dtype=torch.int32)
+    dim_used = dim_used.to(device=batch.device, dtype=torch.int32).contiguous()
+    B, Ttot, Dfull = batch.shape
+    D = dim_used.numel()
+    x, gt = out if out is not None else (torch.empty(B, input_n, D, device=batch.device), torch.empty(B, output_n, D, device=batch.device))
+    with torch.cuda.device_of(batch):
+        _call("mmx_window_split", _p(batch), B, Ttot, Dfull, _p(dim_used), D, input_n, output_n, float(x_scale), float(gt_scale),
+              _p(x), _p(gt), _stream())
+    return x, gt
+
+
+_PCK_THRESH = {}
+
+
+def auc_pck_metric(predictions, targets):
+    """Drop-in for ``h36m.utils.utils_mixer.auc_pck_metric``: area under the PCK curve for thresholds 0.001 ... 0.299.
+    One kernel builds the distance histogram over the 299 thresholds (the reference runs 299 x 6 elementwise kernels); the
+    cumulative sum and the trapezoid rule are tensor ops on 300 elements.  No host synchronisation."""
+    import numpy as np
+    pred, gt = _chk(predictions, "predictions"), _chk(targets, "targets")
+    if pred.shape != gt.shape or pred.shape[-1] != 3:
+        raise RuntimeError("auc_pck_metric: expected two tensors of the same shape (..., n_joints, 3)")
+    dev = pred.device
+    th = _PCK_THRESH.get(dev)
+    if th is None:
+        th = _PCK_THRESH[dev] = torch.from_numpy(np.arange(0.001, 0.3, 0.001).astype(np.float32)).to(dev)
+    n = th.numel()
+    nj = pred.numel() // 3
+    hist = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    with torch.cuda.device_of(pred):
+        _call("mmx_pck_hist", _p(pred), _p(gt), nj, _p(th), n, _p(hist), _stream())
+    pck_values = torch.cumsum(hist[:n], 0).to(torch.float32) / float(nj)
+    return torch.trapz(pck_values, dx=0.001) / 0.299

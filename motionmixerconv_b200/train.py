@@ -326,6 +326,10 @@ class TrainStep:
         pl = self.plan
         pl.x.copy_(x, non_blocking=True)
         self.gt.copy_(gt, non_blocking=True)
+        return self._run_step()
+
+    def _run_step(self):
+        pl = self.plan
         if not self.use_graph:
             self._fwd_bwd()
             if self.world > 1:
@@ -340,6 +344,20 @@ class TrainStep:
             self.graph_b.replay()
         n_joints = pl.pred.numel() // 3
         return (self.loss_sum * (float(self.loss_scale) / n_joints)).reshape(())
+
+    def step_raw(self, batch, dim_used, input_n, output_n, x_scale=1.0, gt_scale=1.0):
+        """One training step straight from the raw dataset window (train_mixer_h36m.py:110-120,179): ``batch`` is
+        [B, >= input_n+output_n, D_full]; the ``dim_used`` gather, the ``/1000`` and the train / target split run as ONE kernel
+        writing into the step's static input buffers (no intermediate tensors)."""
+        B = batch.shape[0]
+        D = len(dim_used)
+        if self.plan is None or self.plan.B != B:
+            self._prepare(torch.empty(B, input_n, D, device=self.device), torch.empty(B, output_n, D, device=self.device))
+        if not isinstance(dim_used, torch.Tensor) or dim_used.device != self.device or dim_used.dtype != torch.int32:
+            dim_used = torch.as_tensor(dim_used, dtype=torch.int32).to(self.device)
+        F_.window_split(batch.to(self.device, non_blocking=True), dim_used, input_n, output_n, x_scale, gt_scale,
+                        out=(self.plan.x, self.gt))
+        return self._run_step()
 
     def _capture(self):
         # warm-up on a side stream (first launches set kernel attributes), then capture

@@ -107,3 +107,49 @@ def test_emulated_harmonic_embedding_exact_angle_doubling():
         arg = (x.reshape(-1, 1) * freq[None, :]).astype(np.float32).astype(np.float64)   # ONE fp32 multiply, then exact
         want = np.concatenate([np.sin(arg), np.cos(arg)], axis=1)
         assert np.abs(m - want).max() <= 4e-7, (ladder, np.abs(m - want).max())
+
+
+def test_emulated_conv_dropout_masks_consistent_between_forward_and_backward():
+    """regularization > 0 in a ConvMixerBlock half: the backward regenerates the forward's Philox masks (finite-difference
+    check of sum(y*r) along random directions, fixed (seed, step))."""
+    import ctypes as C
+    from motionmixerconv_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    B, Cn, T, E = 3, 2, 10, 20
+    kt, kp = 3, 5
+    params = [H.f32(1.0 + 0.2 * rng.standard_normal(E)), H.f32(0.2 * rng.standard_normal(E)),
+              H.f32(0.3 * rng.standard_normal((Cn, Cn, kt, kp))), H.f32(0.1 * rng.standard_normal(Cn)),
+              H.f32(0.5 * rng.standard_normal((2, T))), H.f32(0.5 * rng.standard_normal((T, 2)))]
+    x = H.f32(rng.standard_normal((B, Cn, T, E)))
+    r = H.f32(rng.standard_normal((B, Cn, T, E)))
+    desc = L.MmxConvHalfDesc(B, Cn, T, E, kt, kp, 1, 2, 2, L.MMX_ACT["mish"], 1, 0, 1, 3, L.MmxDropout(0.3, 99, 4, None))
+
+    def table(arrs):
+        t = L.MmxConvHalfParams()
+        for f, a in zip(("ln_w", "ln_b", "conv_w", "conv_b", "se_w1", "se_w2"), arrs):
+            setattr(t, f, H.ptr(a))
+        return t
+
+    def fwd(xx, pp):
+        y = np.empty_like(xx)
+        H.call("mmx_conv_half_fwd", C.byref(desc), C.byref(table(pp)), H.ptr(xx), H.ptr(y), None)
+        return y
+
+    y0 = fwd(x, params)
+    assert np.array_equal(y0, fwd(x, params))
+    grads = [np.zeros_like(p) for p in params]
+    dx = np.empty_like(x)
+    H.call("mmx_conv_half_bwd", C.byref(desc), C.byref(table(params)), C.byref(table(grads)), H.ptr(x), H.ptr(r), H.ptr(dx), None)
+    eps = 1e-2
+    v = H.f32(rng.standard_normal(x.shape))
+    fd = (np.sum(fwd(x + eps * v, params).astype(np.float64) * r) - np.sum(fwd(x - eps * v, params).astype(np.float64) * r)) / (2 * eps)
+    an = float(np.sum(dx.astype(np.float64) * v))
+    assert abs(fd - an) <= 2e-2 * max(abs(an), 1.0), (fd, an)
+    for idx in (2, 3, 0):                                  # conv weight, conv bias, LN weight
+        dv = H.f32(rng.standard_normal(params[idx].shape))
+        pp, pm = list(params), list(params)
+        pp[idx] = H.f32(params[idx] + eps * dv)
+        pm[idx] = H.f32(params[idx] - eps * dv)
+        fd = (np.sum(fwd(x, pp).astype(np.float64) * r) - np.sum(fwd(x, pm).astype(np.float64) * r)) / (2 * eps)
+        an = float(np.sum(grads[idx].astype(np.float64) * dv))
+        assert abs(fd - an) <= 3e-2 * max(abs(an), 1.0), (idx, fd, an)
