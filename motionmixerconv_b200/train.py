@@ -281,6 +281,7 @@ class TrainStep:
         self.gt = None
         self.graph_a = self.graph_b = None
         self.kernel_launches_per_step = 0
+        self._staged, self._copy_stream = None, None      # double-buffered host->device prefetch (step(..., prefetch=...))
 
     # ---- pieces -------------------------------------------------------------------------------
     def _fwd_bwd(self):
@@ -319,14 +320,44 @@ class TrainStep:
         return int(self.step_dev.item())
 
     # ---- public -------------------------------------------------------------------------------
-    def step(self, x, gt):
+    def step(self, x, gt, prefetch=None):
         """x: [B,T,D], gt: [B,To,D] (CUDA or pinned host tensors).  Returns the loss as a 0-d CUDA tensor
-        (mean MPJPE of THIS rank's shard times ``loss_scale``); no host synchronisation."""
+        (mean MPJPE of THIS rank's shard times ``loss_scale``); no host synchronisation.
+
+        ``prefetch=(x_next, gt_next)`` (pinned host tensors): the NEXT step's inputs start their host->device copy on a side
+        stream now, overlapping this step's kernels (what ``DataLoader(pin_memory=True)`` + ``.to(device, non_blocking=True)``
+        gives the reference loop, train_mixer_h36m.py:95-96,111).  The next ``step`` call recognises the same tensors and
+        only pays a device-to-device copy."""
         self._prepare(x, gt)
         pl = self.plan
-        pl.x.copy_(x, non_blocking=True)
-        self.gt.copy_(gt, non_blocking=True)
+        cur = torch.cuda.current_stream(self.device)
+        st = self._staged
+        if st is not None and st["x_src"] is x and st["gt_src"] is gt:
+            cur.wait_event(st["ready"])
+            pl.x.copy_(st["x"], non_blocking=True)
+            self.gt.copy_(st["gt"], non_blocking=True)
+            st["free"].record(cur)
+        else:
+            pl.x.copy_(x, non_blocking=True)
+            self.gt.copy_(gt, non_blocking=True)
+        if prefetch is not None:
+            self._prefetch(*prefetch)
         return self._run_step()
+
+    def _prefetch(self, x_next, gt_next):
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        st = self._staged
+        if st is None or st["x"].shape != x_next.shape or st["gt"].shape != gt_next.shape:
+            st = self._staged = dict(x=torch.empty(x_next.shape, device=self.device), gt=torch.empty(gt_next.shape, device=self.device),
+                                     ready=torch.cuda.Event(), free=torch.cuda.Event(), x_src=None, gt_src=None)
+            st["free"].record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(st["free"])        # the staging buffers were consumed by the step that used them
+            st["x"].copy_(x_next, non_blocking=True)
+            st["gt"].copy_(gt_next, non_blocking=True)
+            st["ready"].record(self._copy_stream)
+        st["x_src"], st["gt_src"] = x_next, gt_next
 
     def _run_step(self):
         pl = self.plan

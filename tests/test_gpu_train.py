@@ -101,3 +101,22 @@ def test_dropout_training_mode():
     with torch.no_grad():
         e = model(x).cpu().numpy()
     np.testing.assert_allclose(e, g.pred_eval, rtol=0, atol=1e-5 * np.abs(g.pred_eval).max())
+
+
+def test_prefetch_pipeline_gives_identical_results():
+    """step(x, gt, prefetch=next) (double-buffered H2D on a copy stream) must train exactly like plain step(x, gt)."""
+    from motionmixerconv_b200.train import TrainStep
+    from tests.synthetic import synthetic_pose_windows
+    g = Golden("mlp_k2")
+    data = [tuple(torch.from_numpy(a).pin_memory() for a in synthetic_pose_windows(64, 10, 10, 66, scale="h36m", seed=s)) for s in range(4)]
+    out = []
+    for mode in ("plain", "prefetch"):
+        ts = TrainStep(_model(g.cfg, g.params), lr=1e-3, weight_decay=1e-5)
+        losses = []
+        for i in range(8):
+            if mode == "plain":
+                losses.append(float(ts.step(*data[i % 4])))
+            else:
+                losses.append(float(ts.step(*data[i % 4], prefetch=data[(i + 1) % 4])))
+        out.append(losses)
+    np.testing.assert_allclose(out[0], out[1], rtol=1e-6)
