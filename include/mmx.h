@@ -145,6 +145,14 @@ int mmx_conv_half_bn_bwd2(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, 
                           const float* coef, const float* x, const float* z, const float* dy, const float* gd, float* dx,
                           void* stream);
 
+/* BatchNorm bookkeeping between the passes (nn.BatchNorm2d semantics; C elements, one tiny launch each instead of ~25 tensor ops):
+ * bn_finalize: sums -> bn = [scale|shift|xs|xo]; running_mean/var updated (momentum, unbiased variance), num_batches_tracked += 1;
+ * bn_coef:     backward sums -> coef = [k1|k2|k3]; g_weight += sum dR*xhat, g_bias += sum dR.  Both zero `sums` on exit (the
+ * accumulating kernels must start from zero).  n = elements per channel (B*T*E). */
+int mmx_bn_finalize(double* sums, int C, double n, const float* w, const float* b, float* running_mean, float* running_var,
+                    long long* num_batches_tracked, float momentum, float eps, float* bn, void* stream);
+int mmx_bn_coef(double* sums, int C, double n, const float* bn, float* coef, float* g_weight, float* g_bias, void* stream);
+
 /* mode_conv="once": the second half of ConvMixerBlock.forward degenerates to y = x + se(x)  (or 2x without SE),
  * conv_mixer_model.py:259-263,287-292.  x, y: [B,C,T,E]; se weights may be null when !use_se. */
 int mmx_se_tail_fwd(int B, int C, int T, int E, int se_hidden, int use_se, int use_max_pooling,

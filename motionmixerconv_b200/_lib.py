@@ -89,6 +89,9 @@ SIGNATURES = {
     "mmx_conv_half_bn_apply": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams)] + [C.c_void_p] * 5),
     "mmx_conv_half_bn_bwd1": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams), C.POINTER(MmxConvHalfParams)] + [C.c_void_p] * 6),
     "mmx_conv_half_bn_bwd2": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams), C.POINTER(MmxConvHalfParams)] + [C.c_void_p] * 8),
+    "mmx_bn_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "mmx_bn_coef": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_se_tail_fwd": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 5),
     "mmx_se_tail_bwd": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 8),
     "mmx_pose_encoder_fwd": (C.c_int, [C.POINTER(MmxEncoderDesc), C.POINTER(MmxEncoderParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -73,4 +73,65 @@ MMX_D void pck_hist_body(Exec& ex, const PckHistArgs& a) {
     });
 }
 
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm2d bookkeeping between the two passes of a BatchNorm half (C <= 8 channels; one tiny CTA each):
+//   finalize: batch sums -> [scale | shift | xs | xo], running statistics (momentum, unbiased variance), counter
+//   coef    : backward sums -> [k1 | k2 | k3], d weight += sum dR*xhat, d bias += sum dR
+// Both zero the sums they consumed, so the accumulating kernels always start from zero.
+// (nn.BatchNorm2d semantics: torch/nn/modules/batchnorm.py; used at conv_mixer_model.py:115-116,141)
+// ------------------------------------------------------------------------------------------
+struct BnFinalizeArgs {
+    double* sums;               // [sum A | sum A^2][C], zeroed on exit
+    const float *w, *b;         // BatchNorm weight / bias [C]
+    float *rm, *rv;             // running_mean / running_var [C] (updated)
+    long long* nbt;             // num_batches_tracked (incremented)
+    float* bn;                  // out: [scale | shift | xs | xo][C]
+    double n;                   // elements per channel (B*T*E)
+    float momentum, eps;
+    int C;
+};
+MMX_D void bn_finalize_body(Exec& ex, const BnFinalizeArgs& a) {
+    ex.phase([&](int tid) {
+        if (tid < a.C) {
+            const int c = tid, C = a.C;
+            const double mean = a.sums[c] / a.n;
+            double var = a.sums[C + c] / a.n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const double rstd = 1.0 / sqrt(var + (double)a.eps);
+            const double scale = (double)a.w[c] * rstd;
+            a.bn[c] = (float)scale;
+            a.bn[C + c] = (float)((double)a.b[c] - mean * scale);
+            a.bn[2 * C + c] = (float)rstd;
+            a.bn[3 * C + c] = (float)(-mean * rstd);
+            a.rm[c] = a.rm[c] * (1.0f - a.momentum) + (float)mean * a.momentum;
+            a.rv[c] = a.rv[c] * (1.0f - a.momentum) + (float)(var * (a.n / (a.n > 1.0 ? a.n - 1.0 : 1.0))) * a.momentum;
+            a.sums[c] = 0.0; a.sums[C + c] = 0.0;
+            if (c == 0) *a.nbt += 1;
+        }
+    });
+}
+
+struct BnCoefArgs {
+    double* sums;               // [sum dR | sum dR*xhat][C], zeroed on exit
+    const float* bn;            // [scale | shift | xs | xo][C]
+    float* coef;                // out: [k1 | k2 | k3][C]
+    float *gw, *gb;             // BatchNorm weight / bias gradient accumulators [C]
+    double n;
+    int C;
+};
+MMX_D void bn_coef_body(Exec& ex, const BnCoefArgs& a) {
+    ex.phase([&](int tid) {
+        if (tid < a.C) {
+            const int c = tid, C = a.C;
+            a.coef[c] = a.bn[c];
+            a.coef[C + c] = (float)(a.sums[c] / a.n);
+            a.coef[2 * C + c] = (float)(a.sums[C + c] / a.n);
+            a.gw[c] += (float)a.sums[C + c];
+            a.gb[c] += (float)a.sums[c];
+            a.sums[c] = 0.0; a.sums[C + c] = 0.0;
+        }
+    });
+}
+
 }  // namespace mmx

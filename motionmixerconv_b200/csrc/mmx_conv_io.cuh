@@ -921,7 +921,7 @@ MMX_HD BnPassSmem bn_pass_smem(const BnPassDims& d) {
     int o = 0;
     auto take = [&](int n) { int r = o; o += round_up(n, 4); return r; };
     L.se1 = take(rr * d.T); L.se2 = take(d.T * rr);
-    L.part = take(ST * kParts); L.part2 = take(ST * kParts);
+    L.part = take(ST * d.C * kParts); L.part2 = take(ST * d.C * kParts);     // per (sequence, channel, frame) row
     L.pool = take(ST); L.gate = take(ST); L.z = take(d.S * rr); L.dq = take(ST); L.dz = take(d.S * rr); L.ds = take(ST);
     L.a_se1 = take(rr * d.T); L.a_se2 = take(d.T * rr); L.a_sum = take(16); L.bn = take(32);
     L.total = o;
@@ -959,23 +959,26 @@ MMX_D void bn_apply_fwd_body(Exec& ex, const BnPassArgs& a) {
         const float* zg = a.z + (size_t)seq0 * C * T * E;
         float* yg = a.y + (size_t)seq0 * C * T * E;
         if (d.use_se) {
-            ex.phase([&](int tid) {
-                for (int i = tid; i < ns * T * kParts; i += nthr) {
-                    const int st = i / kParts, p = i - st * kParts, s = st / T, t = st - s * T;
+            ex.phase([&](int tid) {      // row partials: every thread busy (rows = sequences x channels x frames)
+                for (int i = tid; i < nr * kParts; i += nthr) {
+                    const int r = i / kParts, p = i - r * kParts, c = (r / T) % C;
+                    const float sc = sm[L.bn + c], sh = sm[L.bn + 8 + c];
+                    const float* zr = zg + (size_t)r * E;
                     float acc = 0.0f;
-                    for (int c = 0; c < C; ++c) {
-                        const float sc = sm[L.bn + c], sh = sm[L.bn + 8 + c];
-                        const float* zr = zg + ((size_t)(s * C + c) * T + t) * E;
-                        for (int h = 4 * p; h < E; h += 4 * kParts) {
-                            const int n = imin(4, E - h);
-                            for (int k = 0; k < n; ++k) acc += fmaf(act_fwd<ACT>(zr[h + k]), sc, sh);
-                        }
+                    for (int h = 4 * p; h < E; h += 4 * kParts) {
+                        const int n = imin(4, E - h);
+                        for (int k = 0; k < n; ++k) acc += fmaf(act_fwd<ACT>(zr[h + k]), sc, sh);
                     }
                     sm[L.part + i] = acc;
                 }
             });
             ex.phase([&](int tid) {
-                for (int st = tid; st < ns * T; st += nthr) sm[L.pool + st] = sum_parts(sm + L.part + st * kParts) * invCE;
+                for (int st = tid; st < ns * T; st += nthr) {
+                    const int s = st / T, t = st - s * T;
+                    float acc = 0.0f;
+                    for (int c = 0; c < C; ++c) acc += sum_parts(sm + L.part + ((s * C + c) * T + t) * kParts);
+                    sm[L.pool + st] = acc * invCE;
+                }
             });
             ex.phase([&](int tid) {
                 for (int st = tid; st < ns * T; st += nthr) {
@@ -1017,19 +1020,17 @@ MMX_D void bn_bwd1_body(Exec& ex, const BnPassArgs& a) {
         const float* zg = a.z + (size_t)seq0 * C * T * E;
         const float* dyg = a.dy + (size_t)seq0 * C * T * E;
         if (d.use_se) {
-            ex.phase([&](int tid) {      // squeeze of R and dgate = sum dy*R
-                for (int i = tid; i < ns * T * kParts; i += nthr) {
-                    const int st = i / kParts, p = i - st * kParts, s = st / T, t = st - s * T;
+            ex.phase([&](int tid) {      // squeeze of R and dgate = sum dy*R: row partials
+                for (int i = tid; i < ns * C * T * kParts; i += nthr) {
+                    const int r = i / kParts, p = i - r * kParts, c = (r / T) % C;
+                    const float sc = sm[L.bn + c], sh = sm[L.bn + 8 + c];
+                    const size_t off = (size_t)r * E;
                     float acc = 0.0f, dg = 0.0f;
-                    for (int c = 0; c < C; ++c) {
-                        const float sc = sm[L.bn + c], sh = sm[L.bn + 8 + c];
-                        const size_t off = ((size_t)(s * C + c) * T + t) * E;
-                        for (int h = 4 * p; h < E; h += 4 * kParts) {
-                            const int n = imin(4, E - h);
-                            for (int k = 0; k < n; ++k) {
-                                const float rv = fmaf(act_fwd<ACT>(zg[off + h + k]), sc, sh);
-                                acc += rv; dg = fmaf(dyg[off + h + k], rv, dg);
-                            }
+                    for (int h = 4 * p; h < E; h += 4 * kParts) {
+                        const int n = imin(4, E - h);
+                        for (int k = 0; k < n; ++k) {
+                            const float rv = fmaf(act_fwd<ACT>(zg[off + h + k]), sc, sh);
+                            acc += rv; dg = fmaf(dyg[off + h + k], rv, dg);
                         }
                     }
                     sm[L.part + i] = acc; sm[L.part2 + i] = dg;
@@ -1037,8 +1038,14 @@ MMX_D void bn_bwd1_body(Exec& ex, const BnPassArgs& a) {
             });
             ex.phase([&](int tid) {
                 for (int st = tid; st < ns * T; st += nthr) {
-                    sm[L.pool + st] = sum_parts(sm + L.part + st * kParts) * invCE;
-                    sm[L.dq + st] = sum_parts(sm + L.part2 + st * kParts);
+                    const int s = st / T, t = st - s * T;
+                    float acc = 0.0f, dg = 0.0f;
+                    for (int c = 0; c < C; ++c) {
+                        acc += sum_parts(sm + L.part + ((s * C + c) * T + t) * kParts);
+                        dg += sum_parts(sm + L.part2 + ((s * C + c) * T + t) * kParts);
+                    }
+                    sm[L.pool + st] = acc * invCE;
+                    sm[L.dq + st] = dg;
                 }
             });
             ex.phase([&](int tid) {

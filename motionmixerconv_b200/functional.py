@@ -307,36 +307,27 @@ class _ConvHalfAffine(torch.autograd.Function):
 BN_EPS = 1e-5
 
 
-def bn_forward_passes(desc, tw, x, z, y, sums, bn_w, bn_b, running_mean, running_var, num_batches_tracked, momentum=0.1):
-    """statistics pass -> per-channel vectors (tensor ops on C elements) -> apply pass.  Updates the running statistics
-    as nn.BatchNorm2d does (biased variance to normalise, unbiased for the running estimate).  Returns bn = [scale|shift|xs|xo]."""
+def bn_forward_passes(desc, tw, x, z, y, sums, bn, bn_w, bn_b, running_mean, running_var, num_batches_tracked, momentum=0.1):
+    """statistics pass -> mmx_bn_finalize (per-channel vectors, running statistics as nn.BatchNorm2d: biased variance to
+    normalise, unbiased for the running estimate) -> apply pass.  ``sums`` (float64 [2C]) must be zero on entry and is zero
+    again on exit; ``bn`` (float32 [4C]) receives [scale | shift | xs | xo]."""
     B, Cn, T, E = x.shape
-    n = B * T * E
     st = _stream()
-    sums.zero_()
     _call("mmx_conv_half_bn_stats", C_.byref(desc), C_.byref(tw), _p(x), _p(z), _p(sums), st)
-    mean = sums[:Cn] / n
-    var = (sums[Cn:] / n - mean * mean).clamp_min_(0.0)
-    rstd = torch.rsqrt(var + BN_EPS)
-    scale = bn_w.double() * rstd
-    bn = torch.cat([scale, bn_b.double() - mean * scale, rstd, -mean * rstd]).float()
+    _call("mmx_bn_finalize", _p(sums), Cn, float(B * T * E), _p(bn_w), _p(bn_b), _p(running_mean), _p(running_var),
+          _p(num_batches_tracked), float(momentum), BN_EPS, _p(bn), st)
     _call("mmx_conv_half_bn_apply", C_.byref(desc), C_.byref(tw), _p(bn), _p(x), _p(z), _p(y), st)
-    with torch.no_grad():
-        running_mean.mul_(1.0 - momentum).add_(mean.float(), alpha=momentum)
-        running_var.mul_(1.0 - momentum).add_((var * (n / max(n - 1, 1))).float(), alpha=momentum)
-        num_batches_tracked.add_(1)
     return bn
 
 
-def bn_backward_passes(desc, tw, tg, x, z, dy, dx, bn, gd, sums, n):
-    """pass 1 (SE backward + batch sums) -> coefficients -> pass 2 (BN / conv / LN backward).  Returns (d bn.weight, d bn.bias)."""
+def bn_backward_passes(desc, tw, tg, x, z, dy, dx, bn, gd, sums, coef, gw, gb, n):
+    """pass 1 (SE backward + batch sums) -> mmx_bn_coef (coefficients; gw += d bn.weight, gb += d bn.bias) -> pass 2 (BN / conv /
+    LN backward).  ``sums`` zero on entry and on exit."""
     Cn = bn.numel() // 4
     st = _stream()
-    sums.zero_()
     _call("mmx_conv_half_bn_bwd1", C_.byref(desc), C_.byref(tw), C_.byref(tg), _p(bn), _p(z), _p(dy), _p(gd), _p(sums), st)
-    coef = torch.cat([bn[:Cn].double(), sums[:Cn] / n, sums[Cn:] / n]).float()
+    _call("mmx_bn_coef", _p(sums), Cn, float(n), _p(bn), _p(coef), _p(gw), _p(gb), st)
     _call("mmx_conv_half_bn_bwd2", C_.byref(desc), C_.byref(tw), C_.byref(tg), _p(bn), _p(coef), _p(x), _p(z), _p(dy), _p(gd), _p(dx), st)
-    return sums[Cn:].float(), sums[:Cn].float()
 
 
 class _ConvHalfBN(torch.autograd.Function):
@@ -350,9 +341,10 @@ class _ConvHalfBN(torch.autograd.Function):
         B, C, T, E = x.shape
         desc = conv_half_desc(B, C, T, E, *meta)
         z, y = torch.empty_like(x), torch.empty_like(x)
-        sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        sums = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
+        bn = torch.empty(4 * C, dtype=torch.float32, device=x.device)
         with torch.cuda.device_of(x):
-            bn = bn_forward_passes(desc, conv_half_table(params), x, z, y, sums, bn_w, bn_b, running_mean, running_var, num_batches_tracked)
+            bn_forward_passes(desc, conv_half_table(params), x, z, y, sums, bn, bn_w, bn_b, running_mean, running_var, num_batches_tracked)
         ctx.save_for_backward(x, z, bn, *[q for q in params if q is not None])
         ctx.has = [q is not None for q in params]
         ctx.meta = meta
@@ -369,9 +361,11 @@ class _ConvHalfBN(torch.autograd.Function):
         grads = _zeros_like_many(params)
         dx = torch.empty_like(x)
         gd = torch.empty(B, T, 2, dtype=torch.float32, device=x.device)
-        sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        sums = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
+        coef = torch.empty(3 * C, dtype=torch.float32, device=x.device)
+        dw, db = torch.zeros(C, dtype=torch.float32, device=x.device), torch.zeros(C, dtype=torch.float32, device=x.device)
         with torch.cuda.device_of(x):
-            dw, db = bn_backward_passes(desc, conv_half_table(params), conv_half_table(grads), x, z, dy, dx, bn, gd, sums, B * T * E)
+            bn_backward_passes(desc, conv_half_table(params), conv_half_table(grads), x, z, dy, dx, bn, gd, sums, coef, dw, db, B * T * E)
         return (dx, None, dw, db, None, None, None, *grads)
 
 

@@ -162,8 +162,8 @@ class _ConvMixerPlan:
                     reg = (mb.conv1 if half == 0 else mb.conv2).reg
                     self.bn[len(self.ops)] = dict(
                         reg=reg, z=torch.empty(B, C, T, E, device=dev), gd=torch.empty(B, T, 2, device=dev),
-                        sums=torch.zeros(2 * C, dtype=torch.float64, device=dev), bn=None,
-                        gw=flat.grad_of(reg.weight), gb=flat.grad_of(reg.bias))
+                        sums=torch.zeros(2 * C, dtype=torch.float64, device=dev), bn=torch.zeros(4 * C, device=dev),
+                        coef=torch.zeros(3 * C, device=dev), gw=flat.grad_of(reg.weight), gb=flat.grad_of(reg.bias))
                 self.ops.append(("half", mb, half, F_.conv_half_table(hp), F_.conv_half_table([flat.grad_of(q) for q in hp])))
             if mb.mode_conv != "twice":
                 s1, s2 = mb.se_weights()
@@ -199,8 +199,8 @@ class _ConvMixerPlan:
                 d = self._desc(mb, half, training)
                 if training:
                     reg = b["reg"]
-                    b["bn"] = F_.bn_forward_passes(d, tw, self.acts[i], b["z"], self.acts[i + 1], b["sums"], reg.weight, reg.bias,
-                                                   reg.running_mean, reg.running_var, reg.num_batches_tracked)
+                    F_.bn_forward_passes(d, tw, self.acts[i], b["z"], self.acts[i + 1], b["sums"], b["bn"], reg.weight, reg.bias,
+                                         reg.running_mean, reg.running_var, reg.num_batches_tracked)
                 else:
                     aff = F_.bn_eval_affine(b["reg"])
                     hp = mb.half_params(half)
@@ -226,9 +226,8 @@ class _ConvMixerPlan:
                 b = self.bn[i]
                 d = self._desc(mb, half, True)
                 Bn, Cn, Tn, En = self.acts[i].shape
-                dw, db = F_.bn_backward_passes(d, tw, tg, self.acts[i], b["z"], cur, nxt, b["bn"], b["gd"], b["sums"], Bn * Tn * En)
-                b["gw"].add_(dw)
-                b["gb"].add_(db)
+                F_.bn_backward_passes(d, tw, tg, self.acts[i], b["z"], cur, nxt, b["bn"], b["gd"], b["sums"], b["coef"], b["gw"], b["gb"],
+                                      Bn * Tn * En)
             elif kind == "half":
                 d = self._desc(mb, half, True)
                 L.check(lib, lib.mmx_conv_half_bwd(C.byref(d), C.byref(tw), C.byref(tg), _p(self.acts[i]), _p(cur), _p(nxt), st), "mmx_conv_half_bwd")

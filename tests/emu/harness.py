@@ -7,6 +7,7 @@ here with numpy arrays.  It exists so that indexing / math of the kernels can be
 oracle in a container without a GPU; it is never loaded by the product package.
 """
 import ctypes as C
+from ctypes import c_double as C_double, c_float as C_float
 import os
 import subprocess
 
@@ -247,15 +248,15 @@ class EmuConvMixer:
                     z = np.empty_like(y)
                     sums = np.zeros(2 * C, np.float64)
                     call("mmx_conv_half_bn_stats", _byref(desc), _byref(tw), ptr(self.acts[-1]), ptr(z), sums.ctypes.data, None)
-                    n = B * T * E
-                    mean = sums[:C] / n
-                    var = np.maximum(sums[C:] / n - mean * mean, 0.0)
-                    rstd = 1.0 / np.sqrt(var + 1e-5)
-                    scale = self.p[pre + "weight"].astype(np.float64) * rstd
-                    bn = f32(np.concatenate([scale, self.p[pre + "bias"] - mean * scale, rstd, -mean * rstd]))
+                    bn = np.empty(4 * C, np.float32)
+                    rm, rv = f32(self.running[pre + "running_mean"]), f32(self.running[pre + "running_var"])
+                    nbt = np.array(self.running[pre + "num_batches_tracked"], dtype=np.int64).reshape(1)
+                    call("mmx_bn_finalize", sums.ctypes.data, C, C_double(B * T * E), ptr(self.p[pre + "weight"]), ptr(self.p[pre + "bias"]),
+                         ptr(rm), ptr(rv), nbt.ctypes.data, C_float(0.1), C_float(1e-5), ptr(bn), None)
+                    assert not sums.any()
                     call("mmx_conv_half_bn_apply", _byref(desc), _byref(tw), ptr(bn), ptr(self.acts[-1]), ptr(z), ptr(out), None)
-                    self.running[pre + "running_mean"] = 0.9 * self.running[pre + "running_mean"] + 0.1 * mean
-                    self.running[pre + "running_var"] = 0.9 * self.running[pre + "running_var"] + 0.1 * var * n / (n - 1)
+                    self.running[pre + "running_mean"], self.running[pre + "running_var"] = rm, rv
+                    self.running[pre + "num_batches_tracked"] = nbt[0]
                     self.bn_saved[(i, half)] = (z, bn)
                 else:
                     if self.bn:
@@ -298,12 +299,10 @@ class EmuConvMixer:
                 gd = np.empty((B, T, 2), np.float32)
                 sums = np.zeros(2 * C, np.float64)
                 call("mmx_conv_half_bn_bwd1", _byref(desc), _byref(tw), _byref(tg), ptr(bn), ptr(z), ptr(d_act), ptr(gd), sums.ctypes.data, None)
-                nel = B * T * E
-                coef = f32(np.concatenate([bn[:C].astype(np.float64), sums[:C] / nel, sums[C:] / nel]))
+                coef = np.empty(3 * C, np.float32)
+                call("mmx_bn_coef", sums.ctypes.data, C, C_double(B * T * E), ptr(bn), ptr(coef), ptr(g[pre + "weight"]), ptr(g[pre + "bias"]), None)
                 call("mmx_conv_half_bn_bwd2", _byref(desc), _byref(tw), _byref(tg), ptr(bn), ptr(coef), ptr(self.acts[n]), ptr(z),
                      ptr(d_act), ptr(gd), ptr(dx), None)
-                g[pre + "weight"] += sums[C:].astype(np.float32)
-                g[pre + "bias"] += sums[:C].astype(np.float32)
             elif kind == "half":
                 call("mmx_conv_half_bwd", _byref(self._half_desc(i, half, B)), _byref(self._half_tables(i, half, self.p)),
                      _byref(self._half_tables(i, half, g)), ptr(self.acts[n]), ptr(d_act), ptr(dx), None)
