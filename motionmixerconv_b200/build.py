@@ -55,7 +55,47 @@ def _compile(src, verbose):
     return obj, r.stderr
 
 
+STAMP = LIB + ".stamp"
+
+
+def _source_hash():
+    """Content hash of everything that goes into libmmx.so (sources, headers, flags): the up-to-date check must not depend on
+    file mtimes, which a snapshot copy to another machine may not preserve."""
+    import hashlib
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(os.path.dirname(HERE), "include", "mmx.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def _stamp_ok(digest):
+    try:
+        with open(STAMP) as f:
+            return os.path.exists(LIB) and f.read().strip() == digest
+    except OSError:
+        return False
+
+
 def build(force=False, verbose=False):
+    digest = _source_hash()
+    if not force and not verbose and _stamp_ok(digest):
+        return LIB                      # built from exactly these sources (possibly on another machine)
+    import fcntl
+    os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:      # one builder at a time (torchrun starts N ranks at once)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not verbose and _stamp_ok(digest):
+            return LIB
+        path = _build_locked(force, verbose)
+        with open(STAMP, "w") as f:
+            f.write(digest + "\n")
+        return path
+
+
+def _build_locked(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     if force:
         for f in os.listdir(OBJ):

@@ -242,9 +242,9 @@ MMX_D void conv_corr(int tid, int nthr, const float* in, const float* wtab, int 
 //     acc[co][jj] += sum_{s,t,e} dz[s][co][t][e] * n[s][ci][t+i][e+j0+jj]
 // thread -> (slice, ci, i, jb): j0 = 4*jb; the (s,t) pairs are dealt round-robin to the slices.
 // zpad holds dz at offset (qT, qP) of its padded tile (zero halo), npad the normalised input.
-template <int CP>
-MMX_D void conv_wgrad_acc(float (&acc)[CP][4], int tid, int nthr, const float* zpad, const float* npad, int C,
-                          int kT, int kP, int qT, int qP, int TP, int EP, int ns, int T, int E) {
+template <int CP, int DLT>
+MMX_D void conv_wgrad_acc_d(float (&acc)[CP][4], int tid, int nthr, const float* zpad, const float* npad, int C,
+                            int kT, int kP, int qT, int qP, int TP, int EP, int ns, int T, int E) {
     const int nJB = (kP + 3) >> 2;
     const int n_items = C * kT * nJB;
     const int nsl = imax(1, nthr / n_items);
@@ -254,23 +254,37 @@ MMX_D void conv_wgrad_acc(float (&acc)[CP][4], int tid, int nthr, const float* z
     for (int st = sl; st < ns * T; st += nsl) {
         const int s = st / T, t = st - s * T;
         const float* nrow = npad + ((size_t)(s * C + ci) * TP + t + ii) * EP + 4 * jb;
-        const float* zrow = zpad + ((size_t)(s * C) * TP + qT + t) * EP + qP;
+        const float* zrow = zpad + ((size_t)(s * C) * TP + qT + t) * EP + qP - DLT;    // 16-byte aligned: DLT = qP & 3
         for (int e = 0; e < E; e += 4) {
             const f4 n0 = ld4(nrow + e), n1 = ld4(nrow + e + 4);
             const float nv[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
             MMX_UNROLL
             for (int c = 0; c < CP; ++c) {
                 if (c < C) {
-                    const float* zr = zrow + (size_t)c * TP * EP + e;
+                    // dz[e .. e+3] of channel c: one aligned quad, or two when the interior is not quad-aligned (beyond E: zero halo)
+                    const float* za = zrow + (size_t)c * TP * EP + e;
+                    const f4 a0 = ld4(za);
+                    float zq[8] = {a0.x, a0.y, a0.z, a0.w, 0.0f, 0.0f, 0.0f, 0.0f};
+                    if (DLT > 0) { const f4 a1 = ld4(za + 4); zq[4] = a1.x; zq[5] = a1.y; zq[6] = a1.z; zq[7] = a1.w; }
                     MMX_UNROLL
                     for (int k = 0; k < 4; ++k) {
-                        const float zv = zr[k];   // beyond E: the zero halo
+                        const float zv = zq[DLT + k];
                         MMX_UNROLL
                         for (int jj = 0; jj < 4; ++jj) acc[c][jj] = fmaf(zv, nv[k + jj], acc[c][jj]);
                     }
                 }
             }
         }
+    }
+}
+template <int CP>
+MMX_D void conv_wgrad_acc(float (&acc)[CP][4], int tid, int nthr, const float* zpad, const float* npad, int C,
+                          int kT, int kP, int qT, int qP, int TP, int EP, int ns, int T, int E) {
+    switch (qP & 3) {
+        case 0: conv_wgrad_acc_d<CP, 0>(acc, tid, nthr, zpad, npad, C, kT, kP, qT, qP, TP, EP, ns, T, E); break;
+        case 1: conv_wgrad_acc_d<CP, 1>(acc, tid, nthr, zpad, npad, C, kT, kP, qT, qP, TP, EP, ns, T, E); break;
+        case 2: conv_wgrad_acc_d<CP, 2>(acc, tid, nthr, zpad, npad, C, kT, kP, qT, qP, TP, EP, ns, T, E); break;
+        default: conv_wgrad_acc_d<CP, 3>(acc, tid, nthr, zpad, npad, C, kT, kP, qT, qP, TP, EP, ns, T, E); break;
     }
 }
 
@@ -598,9 +612,19 @@ MMX_D void conv_half_bwd_body(Exec& ex, const ConvHalfBwdArgs& a) {
         ex.phase([&](int tid) {
             if (bn2) {      // Z was saved by the forward statistics pass: no conv recompute
                 const float* zg = a.z + (size_t)seq0 * C * T * E;
-                for (int i = tid; i < nr * E; i += nthr) {
-                    const int r = i / E, e = i - r * E, sc = r / T, t = r - sc * T;
-                    sm[L.zPad + ((size_t)sc * TP + qT + t) * EP + qP + e] = zg[i];
+                if ((E & 3) == 0) {
+                    const int E4q = E >> 2;
+                    for (int i = tid; i < nr * E4q; i += nthr) {
+                        const int r = i / E4q, q = i - r * E4q, sc = r / T, t = r - sc * T;
+                        const f4 v = ld4(zg + (size_t)r * E + 4 * q);
+                        float* o = sm + L.zPad + ((size_t)sc * TP + qT + t) * EP + qP + 4 * q;
+                        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+                    }
+                } else {
+                    for (int i = tid; i < nr * E; i += nthr) {
+                        const int r = i / E, e = i - r * E, sc = r / T, t = r - sc * T;
+                        sm[L.zPad + ((size_t)sc * TP + qT + t) * EP + qP + e] = zg[i];
+                    }
                 }
             } else {
                 conv_corr<CP, EW>(tid, nthr, sm + L.nPad, sm + L.wtab, C, C, kT, kP, TP, EP, ns, T, E,
