@@ -37,26 +37,33 @@ static inline int plan_mlp_block(const MmxMlpBlockDesc* d, bool bwd, MlpDims* ou
     const int forced = env_int(bwd ? "MMX_MLP_S_BWD" : "MMX_MLP_S_FWD", 0);
     const int two_cta_budget = (di.max_smem + 1024) / 2 - 1024 - 1024;   // room for 2 CTAs / SM
     const int row_target = bwd ? 96 : 128;
+    // Two candidates: channel-MLP weights staged in shared memory, or read from global (L1/L2; needs H, ch % 4 == 0).  Large H:
+    // the staged weights leave room for a single sequence per tile (10 rows: GEMM phases with a handful of busy threads),
+    // so take the global-weights layout when it at least doubles the rows per tile.
+    int bestS[2] = {0, 0};
     for (int in_smem = 1; in_smem >= 0; --in_smem) {
         if (!in_smem && ((d->H & 3) || (d->ch & 3))) continue;
         m.w_in_smem = in_smem;
-        int best = 0;
-        for (int budget_pass = 0; budget_pass < 2 && !best; ++budget_pass) {
+        for (int budget_pass = 0; budget_pass < 2 && !bestS[in_smem]; ++budget_pass) {
             const int budget = budget_pass == 0 ? two_cta_budget : di.max_smem;
             for (int S = imax(1, row_target / d->T); S >= 1; --S) {
                 m.S = S;
-                if ((size_t)mlp_block_smem(m, bwd).total * 4 <= (size_t)budget) { best = S; break; }
+                if ((size_t)mlp_block_smem(m, bwd).total * 4 <= (size_t)budget) { bestS[in_smem] = S; break; }
             }
         }
-        if (forced > 0) { m.S = forced; if ((size_t)mlp_block_smem(m, bwd).total * 4 <= (size_t)di.max_smem) best = forced; else best = 0; }
-        if (best) {
-            m.S = imin(best, d->B);
-            const size_t bytes = (size_t)mlp_block_smem(m, bwd).total * 4;
-            const int per_sm = imax(1, imin(8, (int)((di.max_smem + 1024) / (bytes + 1024))));
-            const int ntiles = (d->B + m.S - 1) / m.S;
-            *out = m; *smem = bytes; *grid = balanced_grid(ntiles, di.sms * per_sm);
-            return MMX_OK;
-        }
+        if (forced > 0) { m.S = forced; bestS[in_smem] = (size_t)mlp_block_smem(m, bwd).total * 4 <= (size_t)di.max_smem ? forced : 0; }
+    }
+    int pick = bestS[1] ? 1 : 0;
+    if (bestS[0] >= 2 * imax(bestS[1], 1) && bestS[1] * d->T < 32) pick = 0;
+    if (env_int("MMX_MLP_W_SMEM", -1) >= 0 && bestS[env_int("MMX_MLP_W_SMEM", -1) & 1]) pick = env_int("MMX_MLP_W_SMEM", -1) & 1;
+    if (bestS[pick]) {
+        m.w_in_smem = pick;
+        m.S = imin(bestS[pick], d->B);
+        const size_t bytes = (size_t)mlp_block_smem(m, bwd).total * 4;
+        const int per_sm = imax(1, imin(8, (int)((di.max_smem + 1024) / (bytes + 1024))));
+        const int ntiles = (d->B + m.S - 1) / m.S;
+        *out = m; *smem = bytes; *grid = balanced_grid(ntiles, di.sms * per_sm);
+        return MMX_OK;
     }
     return fail(MMX_E_UNSUPPORTED, "MixerBlock tile does not fit shared memory (H=%d ch=%d)", d->H, d->ch);
 }
