@@ -16,8 +16,6 @@
 
 namespace mmx {
 
-constexpr int kParts = 8;   // partial sums per row / per (sequence, frame) in the reduction phases
-
 struct ConvDims {
     int B, C, T, E;
     int kT, kP, pT, pP;   // kernel (time, embedding) and top / left zero padding ('same': (k-1)/2)
@@ -100,52 +98,6 @@ MMX_HD ConvSmem conv_smem(const ConvDims& d, bool bwd) {
     }
     L.total = o;
     return L;
-}
-
-// ------------------------------------------------------------------------------------------
-// row reductions with kParts threads per row.  Part p handles quads p, p+kParts, ... of the row.
-// ------------------------------------------------------------------------------------------
-MMX_D float row_part_sum(const float* row, int W, int p) {
-    float s = 0.0f;
-    for (int h = 4 * p; h < W; h += 4 * kParts) {
-        const int n = imin(4, W - h);
-        for (int k = 0; k < n; ++k) s += row[h + k];
-    }
-    return s;
-}
-MMX_D float row_part_sqdev(const float* row, int W, float mu, int p) {
-    float s = 0.0f;
-    for (int h = 4 * p; h < W; h += 4 * kParts) {
-        const int n = imin(4, W - h);
-        for (int k = 0; k < n; ++k) { const float dv = row[h + k] - mu; s = fmaf(dv, dv, s); }
-    }
-    return s;
-}
-MMX_D float sum_parts(const float* p) {
-    return ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
-}
-
-// LayerNorm statistics (biased variance, two passes) of `nr` rows of width W -> sm[o_mean..], sm[o_rstd..]
-template <class ExecT>
-MMX_D void ln_stats_phases(ExecT& ex, float* sm, int o_part, int o_part2, int o_mean, int o_rstd,
-                           const float* rows, int pitch, int nr, int W) {
-    const int nthr = ex.nthr;
-    ex.phase([&](int tid) {
-        for (int i = tid; i < nr * kParts; i += nthr)
-            sm[o_part + i] = row_part_sum(rows + (size_t)(i / kParts) * pitch, W, i % kParts);
-    });
-    ex.phase([&](int tid) {
-        for (int i = tid; i < nr * kParts; i += nthr) {
-            const int r = i / kParts, p = i - r * kParts;
-            const float mu = sum_parts(sm + o_part + r * kParts) / (float)W;
-            if (p == 0) sm[o_mean + r] = mu;
-            sm[o_part2 + i] = row_part_sqdev(rows + (size_t)r * pitch, W, mu, p);
-        }
-    });
-    ex.phase([&](int tid) {
-        for (int r = tid; r < nr; r += nthr)
-            sm[o_rstd + r] = 1.0f / sqrtf(sum_parts(sm + o_part2 + r * kParts) / (float)W + 1e-5f);
-    });
 }
 
 // ------------------------------------------------------------------------------------------

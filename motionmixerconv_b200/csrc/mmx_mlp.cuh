@@ -15,6 +15,55 @@
 
 namespace mmx {
 
+constexpr int kParts = 8;   // partial sums per row / per (sequence, frame) in the reduction phases
+
+// ------------------------------------------------------------------------------------------
+// row reductions with kParts threads per row.  Part p handles quads p, p+kParts, ... of the row.
+// ------------------------------------------------------------------------------------------
+MMX_D float row_part_sum(const float* row, int W, int p) {
+    float s = 0.0f;
+    for (int h = 4 * p; h < W; h += 4 * kParts) {
+        const int n = imin(4, W - h);
+        for (int k = 0; k < n; ++k) s += row[h + k];
+    }
+    return s;
+}
+MMX_D float row_part_sqdev(const float* row, int W, float mu, int p) {
+    float s = 0.0f;
+    for (int h = 4 * p; h < W; h += 4 * kParts) {
+        const int n = imin(4, W - h);
+        for (int k = 0; k < n; ++k) { const float dv = row[h + k] - mu; s = fmaf(dv, dv, s); }
+    }
+    return s;
+}
+MMX_D float sum_parts(const float* p) {
+    return ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+}
+
+// LayerNorm statistics (biased variance, two passes) of `nr` rows of width W -> sm[o_mean..], sm[o_rstd..]
+template <class ExecT>
+MMX_D void ln_stats_phases(ExecT& ex, float* sm, int o_part, int o_part2, int o_mean, int o_rstd,
+                           const float* rows, int pitch, int nr, int W) {
+    const int nthr = ex.nthr;
+    ex.phase([&](int tid) {
+        for (int i = tid; i < nr * kParts; i += nthr)
+            sm[o_part + i] = row_part_sum(rows + (size_t)(i / kParts) * pitch, W, i % kParts);
+    });
+    ex.phase([&](int tid) {
+        for (int i = tid; i < nr * kParts; i += nthr) {
+            const int r = i / kParts, p = i - r * kParts;
+            const float mu = sum_parts(sm + o_part + r * kParts) / (float)W;
+            if (p == 0) sm[o_mean + r] = mu;
+            sm[o_part2 + i] = row_part_sqdev(rows + (size_t)r * pitch, W, mu, p);
+        }
+    });
+    ex.phase([&](int tid) {
+        for (int r = tid; r < nr; r += nthr)
+            sm[o_rstd + r] = 1.0f / sqrtf(sum_parts(sm + o_part2 + r * kParts) / (float)W + 1e-5f);
+    });
+}
+
+
 struct MlpDims {
     int B, T, H, tok, ch, rr;  // rr = SE hidden width = T / r_se
     int S;                     // sequences per CTA tile
@@ -44,6 +93,7 @@ struct MlpBlockSmem {
     // per-row / per-sequence small arrays
     int mean1, rstd1, mean2, rstd2, pool1, gate1, pool2, gate2, z1, z2, amax1, amax2;
     int dq, dz, ds1, ds2;
+    int part, part2;                   // kParts partial sums per row (row reductions with several threads per row)
     // gradient accumulators owned by single threads (backward only)
     int a_ln1g, a_ln1b, a_ln2g, a_ln2b, a_cb1, a_cb2, a_se1, a_se2, a_tb1, a_tb2;
     // activation tiles
@@ -70,6 +120,7 @@ MMX_HD MlpBlockSmem mlp_block_smem(const MlpDims& d, bool bwd) {
     L.pool1 = take(L.R); L.gate1 = take(L.R); L.pool2 = take(L.R); L.gate2 = take(L.R);
     L.z1 = take(S * rr); L.z2 = take(S * rr); L.amax1 = take(L.R); L.amax2 = take(L.R);
     L.dq = take(L.R); L.dz = take(S * rr); L.ds1 = take(L.R); L.ds2 = take(L.R);
+    L.part = take(L.R * kParts); L.part2 = take(L.R * kParts);
     if (bwd) {
         L.a_ln1g = take(H); L.a_ln1b = take(H); L.a_ln2g = take(H); L.a_ln2b = take(H);
         L.a_cb1 = take(ch); L.a_cb2 = take(H); L.a_se1 = take(rr * T); L.a_se2 = take(T * rr);
@@ -187,6 +238,46 @@ MMX_D void row_pool(const float* row, int W, int use_max, float* pool, float* am
     }
 }
 
+// SE squeeze of nr rows: mean via kParts partial sums per row (every thread busy), max via one thread per row
+template <class ExecT>
+MMX_D void row_pool_phases(ExecT& ex, float* sm, const float* rows, int pitch, int nr, int W, int use_max, int o_pool, int o_amax, int o_part) {
+    const int nthr = ex.nthr;
+    if (use_max) {
+        ex.phase([&](int tid) {
+            for (int r = tid; r < nr; r += nthr) row_pool(rows + (size_t)r * pitch, W, 1, sm + o_pool + r, sm + o_amax + r);
+        });
+        return;
+    }
+    ex.phase([&](int tid) {
+        for (int i = tid; i < nr * kParts; i += nthr) sm[o_part + i] = row_part_sum(rows + (size_t)(i / kParts) * pitch, W, i % kParts);
+    });
+    ex.phase([&](int tid) {
+        for (int r = tid; r < nr; r += nthr) sm[o_pool + r] = sum_parts(sm + o_part + r * kParts) / (float)W;
+    });
+}
+
+// dot[r] = sum_h A[r][h] * B[r][h] for nr rows, kParts threads per row
+template <class ExecT>
+MMX_D void row_dot_phases(ExecT& ex, float* sm, const float* A, const float* Bm, int pitch, int nr, int W, int o_dot, int o_part) {
+    const int nthr = ex.nthr;
+    ex.phase([&](int tid) {
+        for (int i = tid; i < nr * kParts; i += nthr) {
+            const int r = i / kParts, p = i - r * kParts;
+            const float* ar = A + (size_t)r * pitch;
+            const float* br = Bm + (size_t)r * pitch;
+            float s = 0.0f;
+            for (int h = 4 * p; h < W; h += 4 * kParts) {
+                const int n = imin(4, W - h);
+                for (int k = 0; k < n; ++k) s = fmaf(ar[h + k], br[h + k], s);
+            }
+            sm[o_part + i] = s;
+        }
+    });
+    ex.phase([&](int tid) {
+        for (int r = tid; r < nr; r += nthr) sm[o_dot + r] = sum_parts(sm + o_part + r * kParts);
+    });
+}
+
 // SE excitation for row r = (s,t): gate = sigmoid(S2[t,:] . relu(S1 . pool[s,:])); thread t==0 of the
 // sequence also stores the pre-activation z[s,:] (needed by the backward)
 MMX_D float se_excite(const float* se1, const float* se2, const float* pool_s, int T, int rr, int t, float* z_s) {
@@ -301,9 +392,7 @@ MMX_D void mlp_block_fwd_body(Exec& ex, const MlpBlockFwdArgs& a) {
             for (int i = tid; i < nr * (PH - H); i += nthr) { int r = i / (PH - H); sm[L.bA + r * PH + H + (i - r * (PH - H))] = 0.0f; }
             for (int i = tid; i < nr * (PC - ch); i += nthr) { int r = i / (PC - ch); sm[L.bG + r * PC + ch + (i - r * (PC - ch))] = 0.0f; }
         });
-        ex.phase([&](int tid) {
-            for (int r = tid; r < nr; r += nthr) row_stats(sm + L.bX + r * PH, H, sm + L.mean1 + r, sm + L.rstd1 + r, 1e-5f);
-        });
+        ln_stats_phases(ex, sm, L.part, L.part2, L.mean1, L.rstd1, sm + L.bX, PH, nr, H);
         // token mixing: one thread per (sequence, channel)
         ex.phase([&](int tid) {
             TokenMix<ACT, TC, TOKC> tm;
@@ -316,9 +405,7 @@ MMX_D void mlp_block_fwd_body(Exec& ex, const MlpBlockFwdArgs& a) {
             }
         });
         if (d.use_se) {
-            ex.phase([&](int tid) {
-                for (int r = tid; r < nr; r += nthr) row_pool(sm + L.bA + r * PH, H, d.use_max, sm + L.pool1 + r, sm + L.amax1 + r);
-            });
+            row_pool_phases(ex, sm, sm + L.bA, PH, nr, H, d.use_max, L.pool1, L.amax1, L.part);
             ex.phase([&](int tid) {
                 for (int r = tid; r < nr; r += nthr) {
                     const int s = r / T, t = r - s * T;
@@ -326,16 +413,15 @@ MMX_D void mlp_block_fwd_body(Exec& ex, const MlpBlockFwdArgs& a) {
                 }
             });
         }
-        // X1 = X + gate*Yt ; LN2 statistics (one thread per row)
+        // X1 = X + gate*Yt ; LN2 statistics
         ex.phase([&](int tid) {
-            for (int r = tid; r < nr; r += nthr) {
+            for (int i = tid; i < nr * H; i += nthr) {
+                const int r = i / H, h = i - r * H;
                 const float g = d.use_se ? sm[L.gate1 + r] : 1.0f;
-                float* xr = sm + L.bX + r * PH;
-                const float* yr = sm + L.bA + r * PH;
-                for (int h = 0; h < H; ++h) xr[h] = fmaf(g, yr[h], xr[h]);
-                row_stats(xr, H, sm + L.mean2 + r, sm + L.rstd2 + r, 1e-5f);
+                sm[L.bX + r * PH + h] = fmaf(g, sm[L.bA + r * PH + h], sm[L.bX + r * PH + h]);
             }
         });
+        ln_stats_phases(ex, sm, L.part, L.part2, L.mean2, L.rstd2, sm + L.bX, PH, nr, H);
         ex.phase([&](int tid) {
             for (int i = tid; i < nr * H; i += nthr) {
                 const int r = i / H, h = i - r * H;
@@ -358,9 +444,7 @@ MMX_D void mlp_block_fwd_body(Exec& ex, const MlpBlockFwdArgs& a) {
             });
         });
         if (d.use_se) {
-            ex.phase([&](int tid) {
-                for (int r = tid; r < nr; r += nthr) row_pool(sm + L.bA + r * PH, H, d.use_max, sm + L.pool2 + r, sm + L.amax2 + r);
-            });
+            row_pool_phases(ex, sm, sm + L.bA, PH, nr, H, d.use_max, L.pool2, L.amax2, L.part);
             ex.phase([&](int tid) {
                 for (int r = tid; r < nr; r += nthr) {
                     const int s = r / T, t = r - s * T;
@@ -522,9 +606,7 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
                 sm[L.bG + r * PC + c] = 0.0f; sm[L.bU + r * PC + c] = 0.0f;
             }
         });
-        ex.phase([&](int tid) {
-            for (int r = tid; r < nr; r += nthr) row_stats(sm + L.bX + r * PH, H, sm + L.mean1 + r, sm + L.rstd1 + r, 1e-5f);
-        });
+        ln_stats_phases(ex, sm, L.part, L.part2, L.mean1, L.rstd1, sm + L.bX, PH, nr, H);
         ex.phase([&](int tid) {
             TokenMix<ACT, TC, TOKC> tm;
             for (int p = tid; p < ns * H; p += nthr) {
@@ -536,9 +618,7 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
             }
         });
         if (d.use_se) {
-            ex.phase([&](int tid) {
-                for (int r = tid; r < nr; r += nthr) row_pool(sm + L.bYt + r * PH, H, d.use_max, sm + L.pool1 + r, sm + L.amax1 + r);
-            });
+            row_pool_phases(ex, sm, sm + L.bYt, PH, nr, H, d.use_max, L.pool1, L.amax1, L.part);
             ex.phase([&](int tid) {
                 for (int r = tid; r < nr; r += nthr) {
                     const int s = r / T, t = r - s * T;
@@ -547,15 +627,13 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
             });
         }
         ex.phase([&](int tid) {
-            for (int r = tid; r < nr; r += nthr) {
+            for (int i = tid; i < nr * H; i += nthr) {
+                const int r = i / H, h = i - r * H;
                 const float g = d.use_se ? sm[L.gate1 + r] : 1.0f;
-                const float* xr = sm + L.bX + r * PH;
-                const float* yr = sm + L.bYt + r * PH;
-                float* x1 = sm + L.bX1 + r * PH;
-                for (int h = 0; h < H; ++h) x1[h] = fmaf(g, yr[h], xr[h]);
-                row_stats(x1, H, sm + L.mean2 + r, sm + L.rstd2 + r, 1e-5f);
+                sm[L.bX1 + r * PH + h] = fmaf(g, sm[L.bYt + r * PH + h], sm[L.bX + r * PH + h]);
             }
         });
+        ln_stats_phases(ex, sm, L.part, L.part2, L.mean2, L.rstd2, sm + L.bX1, PH, nr, H);
         ex.phase([&](int tid) {
             for (int i = tid; i < nr * H; i += nthr) {
                 const int r = i / H, h = i - r * H;
@@ -580,16 +658,8 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
         });
         // ---------------- channel half backward ----------------
         if (d.use_se) {
-            ex.phase([&](int tid) {
-                for (int r = tid; r < nr; r += nthr) {
-                    row_pool(sm + L.bY2 + r * PH, H, d.use_max, sm + L.pool2 + r, sm + L.amax2 + r);
-                    float dg = 0.0f;
-                    const float* dr_ = sm + L.bD + r * PH;
-                    const float* yr = sm + L.bY2 + r * PH;
-                    for (int h = 0; h < H; ++h) dg = fmaf(dr_[h], yr[h], dg);
-                    sm[L.dq + r] = dg;
-                }
-            });
+            row_pool_phases(ex, sm, sm + L.bY2, PH, nr, H, d.use_max, L.pool2, L.amax2, L.part);
+            row_dot_phases(ex, sm, sm + L.bD, sm + L.bY2, PH, nr, H, L.dq, L.part2);
             ex.phase([&](int tid) {
                 for (int r = tid; r < nr; r += nthr) {
                     const int s = r / T, t = r - s * T;
@@ -680,34 +750,34 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
                 }
                 sm[L.a_ln2g + h] += sg; sm[L.a_ln2b + h] += sb;
             }
-            for (int r = tid; r < nr; r += nthr) {
+            for (int i = tid; i < nr * kParts; i += nthr) {       // row partials of m1 = sum dxh, m2 = sum dxh*xhat
+                const int r = i / kParts, p = i - r * kParts;
                 const float mu = sm[L.mean2 + r], rs = sm[L.rstd2 + r];
                 const float* dn = sm + L.bY2 + r * PH;
                 const float* x1 = sm + L.bX1 + r * PH;
-                float* dd = sm + L.bD + r * PH;
                 float m1 = 0.0f, m2 = 0.0f;
-                for (int h = 0; h < H; ++h) {
-                    const float dxh = dn[h] * sm[L.ln2_g + h];
-                    m1 += dxh; m2 = fmaf(dxh, (x1[h] - mu) * rs, m2);
+                for (int h = 4 * p; h < H; h += 4 * kParts) {
+                    const int n = imin(4, H - h);
+                    for (int k = 0; k < n; ++k) {
+                        const float dxh = dn[h + k] * sm[L.ln2_g + h + k];
+                        m1 += dxh; m2 = fmaf(dxh, (x1[h + k] - mu) * rs, m2);
+                    }
                 }
-                m1 *= invH; m2 *= invH;
-                for (int h = 0; h < H; ++h) {
-                    const float dxh = dn[h] * sm[L.ln2_g + h];
-                    dd[h] += rs * (dxh - m1 - (x1[h] - mu) * rs * m2);
-                }
+                sm[L.part + i] = m1; sm[L.part2 + i] = m2;
+            }
+        });
+        ex.phase([&](int tid) {
+            for (int i = tid; i < nr * H; i += nthr) {
+                const int r = i / H, h = i - r * H;
+                const float mu = sm[L.mean2 + r], rs = sm[L.rstd2 + r];
+                const float m1 = sum_parts(sm + L.part + r * kParts) * invH, m2 = sum_parts(sm + L.part2 + r * kParts) * invH;
+                const float dxh = sm[L.bY2 + r * PH + h] * sm[L.ln2_g + h];
+                sm[L.bD + r * PH + h] += rs * (dxh - m1 - (sm[L.bX1 + r * PH + h] - mu) * rs * m2);
             }
         });
         // ---------------- token half backward ----------------
         if (d.use_se) {
-            ex.phase([&](int tid) {
-                for (int r = tid; r < nr; r += nthr) {
-                    float dg = 0.0f;
-                    const float* dr_ = sm + L.bD + r * PH;
-                    const float* yr = sm + L.bYt + r * PH;
-                    for (int h = 0; h < H; ++h) dg = fmaf(dr_[h], yr[h], dg);
-                    sm[L.dq + r] = dg;
-                }
-            });
+            row_dot_phases(ex, sm, sm + L.bD, sm + L.bYt, PH, nr, H, L.dq, L.part2);
             se_backward_phases(ex, sm, L, d, ns, L.gate1, L.pool1, L.z1, L.ds1);
         }
         ex.phase([&](int tid) {
@@ -837,22 +907,30 @@ MMX_D void mlp_block_bwd_body(Exec& ex, const MlpBlockBwdArgs& a) {
                 }
                 sm[L.a_ln1g + h] += sg; sm[L.a_ln1b + h] += sb;
             }
-            // LN1 backward, rows: dX = dX1 + LN1'(dN1)   (bD in place)
-            for (int r = tid; r < nr; r += nthr) {
+            // LN1 backward, rows: dX = dX1 + LN1'(dN1): row partials of m1, m2 here, the update in the next phase
+            for (int i = tid; i < nr * kParts; i += nthr) {
+                const int r = i / kParts, p = i - r * kParts;
                 const float mu = sm[L.mean1 + r], rs = sm[L.rstd1 + r];
                 const float* dn = sm + L.bdN1 + r * PH;
                 const float* x0 = sm + L.bX + r * PH;
-                float* dd = sm + L.bD + r * PH;
                 float m1 = 0.0f, m2 = 0.0f;
-                for (int h = 0; h < H; ++h) {
-                    const float dxh = dn[h] * sm[L.ln1_g + h];
-                    m1 += dxh; m2 = fmaf(dxh, (x0[h] - mu) * rs, m2);
+                for (int h = 4 * p; h < H; h += 4 * kParts) {
+                    const int n = imin(4, H - h);
+                    for (int k = 0; k < n; ++k) {
+                        const float dxh = dn[h + k] * sm[L.ln1_g + h + k];
+                        m1 += dxh; m2 = fmaf(dxh, (x0[h + k] - mu) * rs, m2);
+                    }
                 }
-                m1 *= invH; m2 *= invH;
-                for (int h = 0; h < H; ++h) {
-                    const float dxh = dn[h] * sm[L.ln1_g + h];
-                    dd[h] += rs * (dxh - m1 - (x0[h] - mu) * rs * m2);
-                }
+                sm[L.part + i] = m1; sm[L.part2 + i] = m2;
+            }
+        });
+        ex.phase([&](int tid) {
+            for (int i = tid; i < nr * H; i += nthr) {
+                const int r = i / H, h = i - r * H;
+                const float mu = sm[L.mean1 + r], rs = sm[L.rstd1 + r];
+                const float m1 = sum_parts(sm + L.part + r * kParts) * invH, m2 = sum_parts(sm + L.part2 + r * kParts) * invH;
+                const float dxh = sm[L.bdN1 + r * PH + h] * sm[L.ln1_g + h];
+                sm[L.bD + r * PH + h] += rs * (dxh - m1 - (sm[L.bX + r * PH + h] - mu) * rs * m2);
             }
         });
         ex.phase([&](int tid) { store_tile(tid, nthr, dxg, sm + L.bD, nr, H, PH); });
