@@ -84,6 +84,9 @@ static int launch(const Args& a, int grid, int block, size_t smem_bytes, void* s
     if (smem_bytes > 48 * 1024 && conf < smem_bytes) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return fail(MMX_E_CUDA, "cudaFuncSetAttribute(%zu): %s", smem_bytes, cudaGetErrorString(e));
+        // the planners size tiles so that two CTAs fit one SM: ask for the full shared-memory carve-out, otherwise the driver
+        // may pick an L1/shared split that holds only one
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
         conf = smem_bytes;
     }
     kern<<<grid, block, smem_bytes, (cudaStream_t)stream>>>(a);
