@@ -31,6 +31,12 @@ extern "C" {
 #define MMX_ACT_GELU 0
 #define MMX_ACT_MISH 1
 
+/* Arithmetic of the contractions inside a fused block.  FP32: fp32 FMA everywhere (1e-5 parity with the reference).
+ * TF32: tensor-core MMAs with TF32-rounded operands and fp32 accumulation (2e-3 parity); LayerNorm, activations, SE,
+ * residuals and every reduction stay fp32.  TF32 is a permission: shapes the tensor-core kernels do not serve run FP32. */
+#define MMX_PREC_FP32 0
+#define MMX_PREC_TF32 1
+
 int mmx_version(void);
 const char* mmx_last_error(void);
 
@@ -65,6 +71,7 @@ typedef struct {
     int training;         /* dropout active only when training != 0 */
     int block_index;      /* selects the dropout sites of this block */
     MmxDropout dropout;
+    int precision;        /* MMX_PREC_* */
 } MmxMlpBlockDesc;
 
 /* y = MixerBlock(x): LN1 -> token MLP -> SE -> +res -> LN2 -> channel MLP -> SE -> +res, fused.

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmmx.so")
 
 MMX_ACT = {"gelu": 0, "mish": 1}
+MMX_PREC = {"fp32": 0, "tf32": 1}
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -30,7 +31,7 @@ class MmxMlpBlockParams(C.Structure):
 class MmxMlpBlockDesc(C.Structure):
     _fields_ = [("B", C.c_int), ("T", C.c_int), ("H", C.c_int), ("tok", C.c_int), ("ch", C.c_int),
                 ("se_hidden", C.c_int), ("act", C.c_int), ("use_se", C.c_int), ("use_max_pooling", C.c_int),
-                ("training", C.c_int), ("block_index", C.c_int), ("dropout", MmxDropout)]
+                ("training", C.c_int), ("block_index", C.c_int), ("dropout", MmxDropout), ("precision", C.c_int)]
 
 
 class MmxMlpHeadParams(C.Structure):

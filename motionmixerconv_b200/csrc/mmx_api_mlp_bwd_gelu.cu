@@ -6,12 +6,17 @@
 
 int mmx_mlp_bwd_launch_mish(const mmx::MlpBlockBwdArgs& a, int wt1, int grid, size_t smem, void* stream);
 
+bool mmx_mlp_tc_ok(const MmxMlpBlockDesc* d);
+int mmx_mlp_tc_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads,
+                   const float* x, const float* dy, float* dx, void* stream);
+
 extern "C" int mmx_mlp_block_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads,
                                  const float* x, const float* dy, float* dx, void* stream) {
     if (!x || !dy || !dx) return fail(MMX_E_INVALID, "mmx_mlp_block_bwd: null tensor");
     MlpBlockBwdArgs a;
     size_t smem; int grid, nwarp = 0;
     if (!d) return fail(MMX_E_INVALID, "null descriptor");
+    if (mmx_mlp_tc_ok(d)) return mmx_mlp_tc_bwd(d, w, grads, x, dy, dx, stream);
     const bool warp_variant = mlp_warp_variant_ok(d);
     int rc = warp_variant ? plan_mlp_block_warp(d, true, &a.d, &smem, &grid, &nwarp) : plan_mlp_block(d, true, &a.d, &smem, &grid);
     if (rc) return rc;

@@ -8,6 +8,7 @@ takes the stream explicitly, and we re-enter the tensor's device before every ca
 from __future__ import annotations
 
 import ctypes as C
+import os
 import ctypes as C_   # (the conv wrappers use C for the channel count)
 
 import torch
@@ -96,9 +97,27 @@ def mlp_block_table(tensors):
     return t
 
 
-def mlp_block_desc(B, T, H, tok, ch, se_hidden, act, use_se, use_max, training, block_index, p, seed, step, step_dev=None):
+_PRECISION = os.environ.get("MMX_PRECISION", "fp32")
+
+
+def set_precision(precision):
+    """Default arithmetic of the contractions inside the fused MixerBlock kernels: "fp32" (1e-5 parity with the
+    reference) or "tf32" (tensor cores, 2e-3 parity).  A module's own ``precision`` attribute overrides it."""
+    global _PRECISION
+    if precision not in L.MMX_PREC:
+        raise ValueError("unknown precision %r (expected one of %s)" % (precision, sorted(L.MMX_PREC)))
+    _PRECISION = precision
+
+
+def get_precision():
+    return _PRECISION
+
+
+def mlp_block_desc(B, T, H, tok, ch, se_hidden, act, use_se, use_max, training, block_index, p, seed, step, precision=None,
+                   step_dev=None):
     return L.MmxMlpBlockDesc(B, T, H, tok, ch, se_hidden, L.MMX_ACT[act], int(use_se), int(use_max), int(training),
-                             block_index, L.MmxDropout(float(p), int(seed), int(step), step_dev))
+                             block_index, L.MmxDropout(float(p), int(seed), int(step), step_dev),
+                             L.MMX_PREC[precision or _PRECISION])
 
 
 class _MlpBlock(torch.autograd.Function):
@@ -133,7 +152,7 @@ class _MlpBlock(torch.autograd.Function):
 
 
 def mlp_block(x, meta, params):
-    """meta = (tok, ch, se_hidden, act, use_se, use_max, training, block_index, p, seed, step)."""
+    """meta = (tok, ch, se_hidden, act, use_se, use_max, training, block_index, p, seed, step, precision)."""
     return _MlpBlock.apply(x, meta, *params)
 
 

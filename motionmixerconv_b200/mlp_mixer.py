@@ -83,6 +83,7 @@ class MixerBlock(nn.Module):
         self.r_se = r_se
         self.use_max_pooling = use_max_pooling
         self.block_index = 0          # set by MlpMixer; selects this block's dropout sites
+        self.precision = None         # None: functional.get_precision(); "fp32" | "tf32" (not a reference argument)
         self._calls = 0
 
     def kernel_params(self):
@@ -95,7 +96,8 @@ class MixerBlock(nn.Module):
     def meta(self, seed=0, step=0):
         p = self.regularization if self.regularization > 0.0 else 0.0
         return (self.tokens_mlp_dim, self.channels_mlp_dim, self.seq_len // self.r_se if self.use_se else 0,
-                self.activation, self.use_se, self.use_max_pooling, self.training, self.block_index, p, seed, step)
+                self.activation, self.use_se, self.use_max_pooling, self.training, self.block_index, p, seed, step,
+                self.precision)
 
     def forward(self, x):
         if self.regularization == -1.0:
