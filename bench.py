@@ -193,6 +193,9 @@ def run_ours(args, w):
     model = MlpMixer(**w["cfg"]) if w["family"] == "mlp" else ConvMixer(**w["cfg"])
     model.load_state_dict(MT.random_params(w["family"], w["cfg"], 0), strict=True)
     model = model.to(dev).train()
+    prec = args.precision if w["family"] == "mlp" else "fp32"      # the tensor-core MixerBlock kernels serve the MlpMixer path
+    if w["family"] == "mlp":
+        model.set_precision(prec)
     B = w["B"]
     n_batches = 4
     host = [(torch.from_numpy(x).pin_memory(), torch.from_numpy(g).pin_memory()) for x, g in make_data(w, n_batches, 1234 + 1000 * rank)]
@@ -200,7 +203,7 @@ def run_ours(args, w):
     ts = TrainStep(model, lr=1e-3, weight_decay=1e-5, loss_scale=w["loss_scale"], process_group=pg)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 512 MB > 126 MB L2
 
-    def timed(n_steps, data, read_loss):
+    def timed(n_steps, data, read_loss, ts=ts):
         evs = []
         for i in range(n_steps):
             flush.add_(1.0)                       # evict L2 between timed iterations (outside the events)
@@ -235,10 +238,22 @@ def run_ours(args, w):
     t_e2e_ms, _ = timed(args.steps, host, True)
     barrier()
     clocks = sampler.stop()
-    tt = torch.tensor([t_ms, t_e2e_ms], dtype=torch.float64, device=dev)
+    # ---- the other arithmetic mode of the same step (device-resident), for the record ----
+    t_alt_ms, alt = 0.0, None
+    if w["family"] == "mlp" and not args.no_alt_precision:
+        alt = "fp32" if prec == "tf32" else "tf32"
+        model2 = MlpMixer(**w["cfg"])
+        model2.load_state_dict(MT.random_params(w["family"], w["cfg"], 0), strict=True)
+        model2 = model2.to(dev).train().set_precision(alt)
+        ts2 = TrainStep(model2, lr=1e-3, weight_decay=1e-5, loss_scale=w["loss_scale"], process_group=pg)
+        timed(args.warmup, devd, False, ts2)
+        barrier()
+        t_alt_ms, _ = timed(args.steps, devd, False, ts2)
+        barrier()
+    tt = torch.tensor([t_ms, t_e2e_ms, t_alt_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_ms, t_e2e_ms = tt.tolist()
+    t_ms, t_e2e_ms, t_alt_ms = tt.tolist()
 
     # ---- dominant kernel (block backward) timed alone for the roofline ----
     roof = None
@@ -298,7 +313,10 @@ def run_ours(args, w):
                 "peak_source": which, "algorithmic_bytes_per_launch": alg, "kernel_ms": t_k, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "fp32_tflops": flops / (t_k * 1e-3) / 1e12, "fp32_frac": flops / (t_k * 1e-3) / 1e12 / fp32_peak,
-                "note": "fp32 SIMT (1e-5 parity mode): the kernel is bound by the fp32 pipe / latency, not HBM — see DESIGN.md §4"}
+                "note": ("TF32 tensor-core contractions (2e-3 parity mode): the kernel is bound by instruction issue of the fp32 "
+                         "elementwise work between the MMAs (LayerNorm, Mish, dropout, SE) at 6 warps / SM, not by HBM or the tensor pipe"
+                         if prec == "tf32" else
+                         "fp32 SIMT (1e-5 parity mode): the kernel is bound by the fp32 pipe / latency, not HBM") + " — see DESIGN.md §4"}
 
     if rank != 0:
         if world > 1:
@@ -309,8 +327,11 @@ def run_ours(args, w):
     out = {
         "metric": "train sequences/sec", "value": world * B * args.steps / (t_ms * 1e-3), "unit": "sequences/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if prec == "tf32" else "f32", "data": "synthetic",
         "config": {"workload": w["name"], "model": c, "per_gpu_batch": B, "global_batch": B * world,
+                   "precision": ("tf32: MixerBlock contractions on the tensor cores with TF32 operands and fp32 accumulation; LayerNorm, "
+                                 "activations, SE, residuals, loss, Adam and the embed / head kernels fp32 (north star: 2e-3 parity mode)")
+                                if prec == "tf32" else "fp32 everywhere (north star: 1e-5 parity mode)",
                    "parallelism": "dp%d" % world, "optimizer": "Adam lr 1e-3 wd 1e-5 (fused, flat buffers)",
                    "l2": "512 MB L2 flush between timed iterations (outside the CUDA-event pairs)",
                    "step": "CUDA graph A: memset + embed/encoder + block kernels fwd + head + mpjpe + head bwd + block kernels bwd + embed/encoder bwd; [NCCL all-reduce of the flat bucket]; CUDA graph B: fused adam"},
@@ -324,6 +345,9 @@ def run_ours(args, w):
         "clocks": clocks,
         "roofline": roof,
     }
+    if alt:
+        out["other_precision"] = {"precision": alt, "value": world * B * args.steps / (t_alt_ms * 1e-3), "unit": "sequences/s",
+                                  "ms_per_step": t_alt_ms / args.steps}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(w)
     print(json.dumps(out))
@@ -339,6 +363,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("MMX_WORKLOAD", "k2"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=os.environ.get("MMX_BENCH_PRECISION", "fp32"), choices=["fp32", "tf32"],
+                    help="arithmetic of the MixerBlock contractions (north star: fp32 = 1e-5 parity mode, tf32 = 2e-3 parity mode)")
+    ap.add_argument("--no-alt-precision", action="store_true", help="skip the extra timing of the other precision mode")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = WORKLOADS[args.workload]

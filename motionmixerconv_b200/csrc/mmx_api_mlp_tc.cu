@@ -14,7 +14,8 @@ int mmx_mlp_tc_bwd(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, const MmxMl
 }
 #else
 bool mmx_mlp_tc_ok(const MmxMlpBlockDesc* d) {
-    return d->precision == MMX_PREC_TF32 && d->T == tc::kT && d->tok == tc::kTok && d->H >= 8 && d->H <= 50 && d->ch >= 8 && d->ch <= 50 &&
+    const bool want = d->precision == MMX_PREC_TF32 || env_int("MMX_MLP_TC_FP32", 0);   // opt-in: FP32 mode on the 3xTF32 build of the same kernels (1e-5 parity, measured no faster than the SIMT kernels)
+    return want && d->T == tc::kT && d->tok == tc::kTok && d->H >= 8 && d->H <= 50 && d->ch >= 8 && d->ch <= 50 &&
            (d->H & 1) == 0 && !d->use_max_pooling && (!d->use_se || (d->se_hidden >= 1 && d->se_hidden <= tc::kMaxRR)) &&
            !env_int("MMX_MLP_NO_TC", 0);
 }
@@ -28,26 +29,38 @@ static int tc_dims(const MmxMlpBlockDesc* d, MlpDims* m) {
     return MMX_OK;
 }
 
-static int tc_grid(int B, int nwarp) {
+// One CTA per SM.  The unit of work is a warp's group of 3 sequences; with `waves` groups per warp the job needs
+// ceil(groups / waves) warps -- spread over ALL SMs (fewer warps per CTA) rather than packed into fewer CTAs: a warp runs
+// faster with fewer co-resident warps, and the makespan is waves x the per-group latency either way.
+static void tc_shape(int B, int max_warps_per_cta, int* grid, int* nwarp) {
     const DevInfo di = dev_info();
     const int groups = (B + tc::kSeq - 1) / tc::kSeq;
-    const int max_warps = di.sms * nwarp;
+    const int max_warps = di.sms * max_warps_per_cta;
     const int waves = (groups + max_warps - 1) / max_warps;
     const int warps_needed = (groups + waves - 1) / waves;
-    return imax(1, imin(di.sms, (warps_needed + nwarp - 1) / nwarp));
+    int nw = imax(1, imin(max_warps_per_cta, (warps_needed + di.sms - 1) / di.sms));
+    nw = imax(nw, imin(max_warps_per_cta, env_int("MMX_TC_MIN_WARPS", 1)));
+    *nwarp = nw;
+    *grid = imax(1, imin(di.sms, (warps_needed + nw - 1) / nw));
 }
 
 template <class K, class A>
 static int tc_launch(K kern, const A& a, int grid, int nwarp, size_t smem, void* stream) {
-    static size_t configured[64] = {};
+    // cudaFuncSetAttribute once per (kernel, device): several kernels share this instantiation (same pointer type)
+    struct Conf { const void* fn; int dev; size_t smem; };
+    static Conf conf[64];
+    static int nconf = 0;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) dev = 0;
-    if (configured[dev] < smem) {
+    int slot = -1;
+    for (int i = 0; i < nconf; ++i)
+        if (conf[i].fn == (const void*)kern && conf[i].dev == dev) slot = i;
+    if (slot < 0 || conf[slot].smem < smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(MMX_E_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-        configured[dev] = smem;
+        if (slot < 0 && nconf < 64) slot = nconf++;
+        if (slot >= 0) { conf[slot].fn = (const void*)kern; conf[slot].dev = dev; conf[slot].smem = smem; }
     }
     kern<<<grid, nwarp * 32, smem, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
@@ -62,11 +75,14 @@ int mmx_mlp_tc_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const f
     if ((rc = check_block_params(w, d->use_se, "mmx_mlp_block_fwd"))) return rc;
     a.dr = make_dropout(d->dropout, d->training);
     a.w = to_w(w); a.x = x; a.y = y;
-    const int nwarp = tc::kFwdWarps;
+    int grid, nwarp;
+    tc_shape(d->B, tc::kFwdWarps, &grid, &nwarp);
     const size_t smem = (size_t)tc::smem_layout(false, nwarp).total * 4;
-    const int grid = tc_grid(d->B, nwarp);
-    return d->act == MMX_ACT_GELU ? tc_launch(tc::mlp_block_fwd_tc_kernel<ACT_GELU>, a, grid, nwarp, smem, stream)
-                                  : tc_launch(tc::mlp_block_fwd_tc_kernel<ACT_MISH>, a, grid, nwarp, smem, stream);
+    if (d->precision == MMX_PREC_TF32)
+        return d->act == MMX_ACT_GELU ? tc_launch(tc::mlp_block_fwd_tc_kernel<ACT_GELU, 1>, a, grid, nwarp, smem, stream)
+                                      : tc_launch(tc::mlp_block_fwd_tc_kernel<ACT_MISH, 1>, a, grid, nwarp, smem, stream);
+    return d->act == MMX_ACT_GELU ? tc_launch(tc::mlp_block_fwd_tc_kernel<ACT_GELU, 3>, a, grid, nwarp, smem, stream)
+                                  : tc_launch(tc::mlp_block_fwd_tc_kernel<ACT_MISH, 3>, a, grid, nwarp, smem, stream);
 }
 
 int mmx_mlp_tc_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads,
@@ -78,11 +94,14 @@ int mmx_mlp_tc_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const M
     if ((rc = check_block_params(grads, d->use_se, "mmx_mlp_block_bwd(grads)"))) return rc;
     a.dr = make_dropout(d->dropout, d->training);
     a.w = to_w(w); a.g = to_w(grads); a.x = x; a.dy = dy; a.dx = dx;
-    const int nwarp = tc::kBwdWarps;
+    int grid, nwarp;
+    tc_shape(d->B, tc::kBwdWarps, &grid, &nwarp);
     const size_t smem = (size_t)tc::smem_layout(true, nwarp).total * 4;
     if (smem > (size_t)dev_info().max_smem) return fail(MMX_E_UNSUPPORTED, "MixerBlock (tensor-core variant) does not fit shared memory");
-    const int grid = tc_grid(d->B, nwarp);
-    return d->act == MMX_ACT_GELU ? tc_launch(tc::mlp_block_bwd_tc_kernel<ACT_GELU>, a, grid, nwarp, smem, stream)
-                                  : tc_launch(tc::mlp_block_bwd_tc_kernel<ACT_MISH>, a, grid, nwarp, smem, stream);
+    if (d->precision == MMX_PREC_TF32)
+        return d->act == MMX_ACT_GELU ? tc_launch(tc::mlp_block_bwd_tc_kernel<ACT_GELU, 1>, a, grid, nwarp, smem, stream)
+                                      : tc_launch(tc::mlp_block_bwd_tc_kernel<ACT_MISH, 1>, a, grid, nwarp, smem, stream);
+    return d->act == MMX_ACT_GELU ? tc_launch(tc::mlp_block_bwd_tc_kernel<ACT_GELU, 3>, a, grid, nwarp, smem, stream)
+                                  : tc_launch(tc::mlp_block_bwd_tc_kernel<ACT_MISH, 3>, a, grid, nwarp, smem, stream);
 }
 #endif

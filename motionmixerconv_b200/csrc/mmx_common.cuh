@@ -121,14 +121,17 @@ MMX_HD int pitch_of(int w) {
 // ------------------------------------------------------------------------------------------
 enum { ACT_GELU = 0, ACT_MISH = 1 };
 
-// exp / divide of the activations: MUFU-based intrinsics on the GPU (<= 2 ulp + 2^-21 relative: two orders of
-// magnitude inside the 1e-5 parity bar; checked by the GPU parity tests), libm in the emulator
+// exp / divide of the activations: one MUFU each on the GPU (ex2.approx.ftz / rcp.approx.ftz: <= 2 ulp, no denormal
+// fix-up instructions; two orders of magnitude inside the 1e-5 parity bar, checked by the GPU parity tests), libm in the
+// emulator
 #if defined(MMX_HOST_EMU)
 MMX_D float fast_exp(float x) { return expf(x); }
 MMX_D float fast_div(float a, float b) { return a / b; }
+MMX_D float fast_rcp(float b) { return 1.0f / b; }
 #else
-MMX_D float fast_exp(float x) { return __expf(x); }
-MMX_D float fast_div(float a, float b) { return __fdividef(a, b); }
+MMX_D float fast_exp(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f)); return r; }
+MMX_D float fast_rcp(float b) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return r; }
+MMX_D float fast_div(float a, float b) { return a * fast_rcp(b); }
 #endif
 
 template <int ACT>
@@ -136,11 +139,11 @@ MMX_D float act_fwd(float u) {
     if (ACT == ACT_GELU) {
         return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f));
     } else {
-        // u * tanh(softplus(u)); tanh(log(1+e)) = n/(n+2) with n = e*(e+2); softplus threshold 20
-        if (u > 20.0f) return u;
-        float e = fast_exp(u);
+        // u * tanh(softplus(u)); tanh(log(1+e)) = n/(n+2) with n = e*(e+2).  softplus threshold 20: beyond it e is
+        // clamped to exp(20), where n/(n+2) rounds to exactly 1 -> returns u (branch-free)
+        float e = fast_exp(fminf(u, 20.0f));
         float n = e * (e + 2.0f);
-        return u * fast_div(n, n + 2.0f);
+        return u * (n * fast_rcp(n + 2.0f));
     }
 }
 
@@ -152,15 +155,15 @@ MMX_D float act_fwd_grad(float u, float* a) {
         *a = u * cdf;
         return cdf + u * fast_exp(-0.5f * u * u) * 0.39894228040143268f;
     } else {
-        if (u > 20.0f) { *a = u; return 1.0f; }
-        float e = fast_exp(u);
+        // mish'(u) = e * w / (n+2)^2,  w = 4(u+1) + e*(4u + 6 + e*(4 + e))   (two MUFUs, branch-free; e clamped at exp(20),
+        // where the value rounds to 1 like the reference's softplus threshold branch)
+        float uc = fminf(u, 20.0f);
+        float e = fast_exp(uc);
         float n = e * (e + 2.0f);
-        float inv = fast_div(1.0f, n + 2.0f);
-        float t = n * inv;                        // tanh(softplus(u))
-        float omt2 = 4.0f * (n + 1.0f) * inv * inv;  // 1 - t^2
-        float sig = fast_div(e, 1.0f + e);
-        *a = u * t;
-        return t + u * omt2 * sig;
+        float inv = fast_rcp(n + 2.0f);
+        float w = fmaf(e, fmaf(e, 4.0f + e, fmaf(4.0f, uc, 6.0f)), 4.0f * (uc + 1.0f));
+        *a = u * (n * inv);
+        return (e * inv) * (w * inv);
     }
 }
 

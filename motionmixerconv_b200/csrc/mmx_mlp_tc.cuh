@@ -42,16 +42,17 @@ constexpr int kPW = 60;            // channel weight pitch (zero padded to 56 + 
 constexpr int kHP = 56;            // padded H / ch extent (7 n8 tiles)
 constexpr int kNT = 7;
 constexpr int kPAcc = 56;          // pitch of the CTA-shared dV accumulators
+constexpr int kAccRows = 52;       // their rows (H, ch <= 50)
 constexpr int kTile = kRows * kPA; // 1664 floats
 constexpr int kPT = 24;            // pitch of the token weight-gradient operand tiles [64][24]
 constexpr int kMaxRR = 2;          // SE bottleneck widths served by this variant (seq_len // r_se)
-constexpr int kFwdWarps = 8, kBwdWarps = 6;
+constexpr int kFwdWarps = 8, kBwdWarps = 8;
 
 struct Smem {
     int v1, v2, c1, c2, g1, b1, tb1, tb2, w1f, w2f, w2g, w1g, se1, se2;
-    int accV1, accV2, locks;
+    int accV1, accV2, wln1, locks;
     int warp0, wstride;
-    int xs, ns, gs, ds, pool, gate, dsh, dgs, rs2, wse, wln1;   // offsets inside a warp's region
+    int xs, ns, gs, ds, pool, gate, dsh, rs2, wse, kb;   // offsets inside a warp's region
     int total;
 };
 
@@ -66,25 +67,29 @@ MMX_HD Smem smem_layout(bool bwd, int nwarp) {
     L.se1 = take(kMaxRR * kT); L.se2 = take(kT * kMaxRR);
     if (bwd) {
         L.w2g = take(6 * 64); L.w1g = take(6 * 64);
-        L.accV1 = take(kHP * kPAcc); L.accV2 = take(kHP * kPAcc); L.locks = take(8);
-    } else L.w2g = L.w1g = L.accV1 = L.accV2 = L.locks = -1;
+        L.accV1 = take(kAccRows * kPAcc); L.accV2 = take(kAccRows * kPAcc); L.wln1 = take(128); L.locks = take(12);
+    } else L.w2g = L.w1g = L.accV1 = L.accV2 = L.wln1 = L.locks = -1;
     L.warp0 = o;
     int w = 0;
     auto wtake = [&](int n) { int r = w; w += round_up(n, 4); return r; };
-    L.xs = wtake(kTile); L.ns = wtake(kTile);
-    if (bwd) { L.gs = wtake(kTile); L.ds = wtake(kTile); } else L.gs = L.ds = -1;
+    // forward: xs (X, then X1) + ns (xhat2).  backward: X^T fragments come straight from global memory (L2), tiles ns, gs, ds
+    if (bwd) { L.xs = -1; L.ns = wtake(kTile); L.gs = wtake(kTile); L.ds = wtake(kTile); }
+    else { L.xs = wtake(kTile); L.ns = wtake(kTile); L.gs = L.ds = -1; }
     L.pool = wtake(32); L.gate = wtake(32);
     if (bwd) {
-        L.dsh = wtake(32); L.dgs = wtake(32); L.rs2 = wtake(32);
-        L.wse = wtake(kSeq * 2 * kMaxRR * kT); L.wln1 = wtake(128);
-    } else L.dsh = L.dgs = L.rs2 = L.wse = L.wln1 = -1;
+        L.dsh = wtake(32); L.rs2 = wtake(32);
+        L.wse = wtake(kSeq * 2 * kMaxRR * kT);
+    } else L.dsh = L.rs2 = L.wse = -1;
+    L.kb = -1;
     L.wstride = w;
     L.total = o + nwarp * w + 64;      // slack: fragment reads run up to 12 floats past the last tile
     return L;
 }
 
 // ------------------------------------------------------------------------------------------ primitives
-MMX_D uint32_t tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+// round-to-nearest (ties away) TF32: the tensor core ignores the 13 low mantissa bits, so adding half a TF32 ulp to the bit
+// pattern is the whole conversion (cvt.rna.tf32.f32 compiles to 4 instructions: it also handles Inf/NaN, which never occur here)
+MMX_D uint32_t tf32(float x) { return __float_as_uint(x) + 0x1000u; }
 MMX_D float tf32f(float x) { return __uint_as_float(tf32(x)); }
 
 // D += A(16x8, row) * B(8x8, col), TF32 in, fp32 accumulate.  Lane (g = lane>>2, t4 = lane&3) holds
@@ -95,9 +100,47 @@ MMX_D void mma8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// Operand fragments.  NX = 1: one MMA on TF32-rounded operands (2e-3 mode).  NX = 3: "3xTF32" error compensation -- every
+// operand is split x = hi + lo (hi = x truncated to TF32, lo = x - hi, exact in fp32) and the product is accumulated as
+// lo*hi + hi*lo + hi*hi (the dropped lo*lo term and the TF32 truncation of lo are both ~2^-22 relative): fp32-grade
+// contractions on the tensor cores, for the 1e-5 mode.
+template <int NX> struct AFrag { uint32_t hi[4]; uint32_t lo[NX == 3 ? 4 : 1]; };
+template <int NX> struct BFrag { uint32_t hi[2]; uint32_t lo[NX == 3 ? 2 : 1]; };
+MMX_D void split3(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+// v0..v3 in A-fragment order
+template <int NX>
+MMX_D void prep_a(float v0, float v1, float v2, float v3, AFrag<NX>& a) {
+    if (NX == 1) { a.hi[0] = tf32(v0); a.hi[1] = tf32(v1); a.hi[2] = tf32(v2); a.hi[3] = tf32(v3); }
+    else { split3(v0, a.hi[0], a.lo[0]); split3(v1, a.hi[1], a.lo[1]); split3(v2, a.hi[2], a.lo[2 % (NX == 3 ? 4 : 1)]); split3(v3, a.hi[3], a.lo[3 % (NX == 3 ? 4 : 1)]); }
+}
+// weights: already rounded to TF32 by stage() when NX == 1
+template <int NX>
+MMX_D void prep_b_w(float b0, float b1, BFrag<NX>& b) {
+    if (NX == 1) { b.hi[0] = __float_as_uint(b0); b.hi[1] = __float_as_uint(b1); }
+    else { split3(b0, b.hi[0], b.lo[0]); split3(b1, b.hi[1], b.lo[1 % (NX == 3 ? 2 : 1)]); }
+}
+// activations used as a B operand
+template <int NX>
+MMX_D void prep_b_a(float b0, float b1, BFrag<NX>& b) {
+    if (NX == 1) { b.hi[0] = tf32(b0); b.hi[1] = tf32(b1); }
+    else { split3(b0, b.hi[0], b.lo[0]); split3(b1, b.hi[1], b.lo[1 % (NX == 3 ? 2 : 1)]); }
+}
+template <int NX>
+MMX_D void mmaX(float (&d)[4], const AFrag<NX>& a, const BFrag<NX>& b) {
+    if (NX == 3) {
+        uint32_t alo[4] = {a.lo[0], a.lo[1 % (NX == 3 ? 4 : 1)], a.lo[2 % (NX == 3 ? 4 : 1)], a.lo[3 % (NX == 3 ? 4 : 1)]};
+        mma8(d, alo, b.hi[0], b.hi[1]);
+        mma8(d, a.hi, b.lo[0], b.lo[1 % (NX == 3 ? 2 : 1)]);
+    }
+    mma8(d, a.hi, b.hi[0], b.hi[1]);
+}
 // An accumulator tile re-used as the A operand of the next contraction: K slot j < 4 carries the tile's column 2j,
 // slot j+4 column 2j+1 -- the B operand of that contraction is staged with the same permutation.
-MMX_D void a_from_c(const float (&c)[4], uint32_t (&a)[4]) { a[0] = tf32(c[0]); a[1] = tf32(c[2]); a[2] = tf32(c[1]); a[3] = tf32(c[3]); }
+template <int NX>
+MMX_D void a_from_c(const float (&c)[4], AFrag<NX>& a) { prep_a<NX>(c[0], c[2], c[1], c[3], a); }
 
 MMX_D float ldf2x(const float* p) { return p[0]; }
 
@@ -223,8 +266,22 @@ MMX_D void load_xT(const float* tile, int rb, int H, int g, int t4, float (&x)[4
             }
 }
 
+// the same fragments straight from global memory (xseq = first float of the sequence, null for a dead sequence): for a
+// fixed register the 8 lanes of a row-group read 32 contiguous bytes -> every sector fetched is fully used
+MMX_D void load_xT_global(const float* xseq, int H, int g, int t4, float (&x)[4][2][4]) {
+    MMX_UNROLL
+    for (int mt = 0; mt < 4; ++mt)
+        MMX_UNROLL
+        for (int nt = 0; nt < 2; ++nt)
+            MMX_UNROLL
+            for (int r = 0; r < 4; ++r) {
+                const int h = 16 * mt + g + 8 * (r >> 1), t = 8 * nt + 2 * t4 + (r & 1);
+                x[mt][nt][r] = (xseq != nullptr && h < H && t < kT) ? __ldg(xseq + t * H + h) : 0.0f;
+            }
+}
+
 struct TokW {            // token-MLP B fragments + biases of this lane
-    uint32_t w1[2][3][2], w2[3][2][2];
+    float w1[2][3][2], w2[3][2][2];
     float b1v[3][2], b2v[2][2];
 };
 MMX_D void load_tokw(const Ctx& cx, TokW& w) {
@@ -233,14 +290,14 @@ MMX_D void load_tokw(const Ctx& cx, TokW& w) {
         MMX_UNROLL
         for (int nt = 0; nt < 3; ++nt) {
             const float2 v = *reinterpret_cast<const float2*>(cx.sm + cx.L.w1f + (kk * 3 + nt) * 64 + cx.lane * 2);
-            w.w1[kk][nt][0] = __float_as_uint(v.x); w.w1[kk][nt][1] = __float_as_uint(v.y);
+            w.w1[kk][nt][0] = v.x; w.w1[kk][nt][1] = v.y;
         }
     MMX_UNROLL
     for (int kk = 0; kk < 3; ++kk)
         MMX_UNROLL
         for (int nt = 0; nt < 2; ++nt) {
             const float2 v = *reinterpret_cast<const float2*>(cx.sm + cx.L.w2f + (kk * 2 + nt) * 64 + cx.lane * 2);
-            w.w2[kk][nt][0] = __float_as_uint(v.x); w.w2[kk][nt][1] = __float_as_uint(v.y);
+            w.w2[kk][nt][0] = v.x; w.w2[kk][nt][1] = v.y;
         }
     MMX_UNROLL
     for (int nt = 0; nt < 3; ++nt) { w.b1v[nt][0] = cx.sm[cx.L.tb1 + 8 * nt + 2 * cx.t4]; w.b1v[nt][1] = cx.sm[cx.L.tb1 + 8 * nt + 2 * cx.t4 + 1]; }
@@ -249,6 +306,7 @@ MMX_D void load_tokw(const Ctx& cx, TokW& w) {
 }
 
 // token fc1 for one m16 tile of hidden rows: u = b1 + N1 W1^T, N1 = xhat*gamma1 + beta1 (xhat already normalised)
+template <int NX>
 MMX_D void token_fc1(const Ctx& cx, const TokW& w, const float (&xh)[2][4], int mt, float (&u)[3][4]) {
     const float ga0 = cx.sm[cx.L.g1 + 16 * mt + cx.g], ga1 = cx.sm[cx.L.g1 + 16 * mt + cx.g + 8];
     const float be0 = cx.sm[cx.L.b1 + 16 * mt + cx.g], be1 = cx.sm[cx.L.b1 + 16 * mt + cx.g + 8];
@@ -256,29 +314,31 @@ MMX_D void token_fc1(const Ctx& cx, const TokW& w, const float (&xh)[2][4], int 
     for (int nt = 0; nt < 3; ++nt) { u[nt][0] = w.b1v[nt][0]; u[nt][1] = w.b1v[nt][1]; u[nt][2] = w.b1v[nt][0]; u[nt][3] = w.b1v[nt][1]; }
     MMX_UNROLL
     for (int kk = 0; kk < 2; ++kk) {
-        uint32_t a[4];
-        a[0] = tf32(fmaf(xh[kk][0], ga0, be0)); a[1] = tf32(fmaf(xh[kk][2], ga1, be1));
-        a[2] = tf32(fmaf(xh[kk][1], ga0, be0)); a[3] = tf32(fmaf(xh[kk][3], ga1, be1));
+        AFrag<NX> a;
+        prep_a<NX>(fmaf(xh[kk][0], ga0, be0), fmaf(xh[kk][2], ga1, be1), fmaf(xh[kk][1], ga0, be0), fmaf(xh[kk][3], ga1, be1), a);
         MMX_UNROLL
-        for (int nt = 0; nt < 3; ++nt) mma8(u[nt], a, w.w1[kk][nt][0], w.w1[kk][nt][1]);
+        for (int nt = 0; nt < 3; ++nt) { BFrag<NX> b; prep_b_w<NX>(w.w1[kk][nt][0], w.w1[kk][nt][1], b); mmaX<NX>(u[nt], a, b); }
     }
 }
+template <int NX>
 MMX_D void token_fc2(const TokW& w, const float (&gv)[3][4], float (&y)[2][4]) {
     MMX_UNROLL
     for (int nt = 0; nt < 2; ++nt) { y[nt][0] = w.b2v[nt][0]; y[nt][1] = w.b2v[nt][1]; y[nt][2] = w.b2v[nt][0]; y[nt][3] = w.b2v[nt][1]; }
     MMX_UNROLL
     for (int kk = 0; kk < 3; ++kk) {
-        uint32_t a[4];
-        a_from_c(gv[kk], a);
+        AFrag<NX> a;
+        a_from_c<NX>(gv[kk], a);
         MMX_UNROLL
-        for (int nt = 0; nt < 2; ++nt) mma8(y[nt], a, w.w2[kk][nt][0], w.w2[kk][nt][1]);
+        for (int nt = 0; nt < 2; ++nt) { BFrag<NX> b; prep_b_w<NX>(w.w2[kk][nt][0], w.w2[kk][nt][1], b); mmaX<NX>(y[nt], a, b); }
     }
 }
 
 // Token half forward of one sequence.  in: x tile rows rb..; out: x = X1 (T orientation), LN2 statistics of its 4 frames.
-template <int ACT>
-MMX_D void token_fwd(const Ctx& cx, const TokW& w, const float* xtile, int rb, uint32_t seq, float (&x)[4][2][4], float (&mu2)[4], float (&rs2)[4]) {
-    load_xT(xtile, rb, cx.H, cx.g, cx.t4, x);
+template <int ACT, int NX>
+MMX_D void token_fwd(const Ctx& cx, const TokW& w, const float* xtile, int rb, const float* xglobal, bool from_global, uint32_t seq,
+                     float (&x)[4][2][4], float (&mu2)[4], float (&rs2)[4]) {
+    if (from_global) load_xT_global(xglobal, cx.H, cx.g, cx.t4, x);
+    else load_xT(xtile, rb, cx.H, cx.g, cx.t4, x);
     float mu[4], rs[4];
     col_stats(x, cx.H, cx.invH, cx.g, mu, rs);
     uint32_t bits0[2], bits1[1];
@@ -293,12 +353,12 @@ MMX_D void token_fwd(const Ctx& cx, const TokW& w, const float* xtile, int rb, u
             MMX_UNROLL
             for (int r = 0; r < 4; ++r) { const int c = nt * 2 + (r & 1); xh[nt][r] = (x[mt][nt][r] - mu[c]) * rs[c]; }
         float u[3][4];
-        token_fc1(cx, w, xh, mt, u);
+        token_fc1<NX>(cx, w, xh, mt, u);
         MMX_UNROLL
         for (int nt = 0; nt < 3; ++nt)
             MMX_UNROLL
             for (int r = 0; r < 4; ++r) u[nt][r] = act_fwd<ACT>(u[nt][r]) * keepf(bits0, mt * 12 + nt * 4 + r, cx.dr.scale);
-        token_fc2(w, u, y[mt]);
+        token_fc2<NX>(w, u, y[mt]);
         MMX_UNROLL
         for (int nt = 0; nt < 2; ++nt)
             MMX_UNROLL
@@ -349,14 +409,15 @@ MMX_D void load_group(float* tile, const float* src, int nvalid /*floats*/, int 
 }
 
 // stage weights (all threads of the CTA).  Channel weights are rounded to TF32 once here.
-MMX_D void stage(float* sm, const Smem& L, const MlpDims& d, const MlpBlockW& w, bool bwd, int tid, int nthr) {
+MMX_D void stage(float* sm, const Smem& L, const MlpDims& d, const MlpBlockW& w, bool bwd, bool round_w, int tid, int nthr) {
     const int H = d.H, ch = d.ch, rr = d.rr;
+    auto rw = [&](float v) { return round_w ? tf32f(v) : v; };
     for (int i = tid; i < L.total; i += nthr) sm[i] = 0.0f;
     __syncthreads();
     for (int i = tid; i < kHP * kPW; i += nthr) {
         const int r = i / kPW, c = i - r * kPW;
-        if (r < ch && c < H) sm[L.v1 + i] = tf32f(w.cw1[r * H + c] * w.ln2_g[c]);      // V1'[c][h] = V1[c][h] * gamma2[h]
-        if (r < H && c < ch) sm[L.v2 + i] = tf32f(w.cw2[r * ch + c]);
+        if (r < ch && c < H) sm[L.v1 + i] = rw(w.cw1[r * H + c] * w.ln2_g[c]);      // V1'[c][h] = V1[c][h] * gamma2[h]
+        if (r < H && c < ch) sm[L.v2 + i] = rw(w.cw2[r * ch + c]);
     }
     for (int i = tid; i < 64; i += nthr) {
         if (i < ch) {
@@ -372,20 +433,20 @@ MMX_D void stage(float* sm, const Smem& L, const MlpDims& d, const MlpBlockW& w,
         const int f = i >> 6, lane = (i >> 1) & 31, j = i & 1, g = lane >> 2, t4 = lane & 3;
         {   // fc1 B: (kk < 2, nt < 3): W1[k = 8nt+g][t = 8kk+2t4+j]
             const int kk = f / 3, nt = f - kk * 3, k = 8 * nt + g, t = 8 * kk + 2 * t4 + j;
-            sm[L.w1f + i] = (k < kTok && t < kT) ? tf32f(w.tw1[k * kT + t]) : 0.0f;
+            sm[L.w1f + i] = (k < kTok && t < kT) ? rw(w.tw1[k * kT + t]) : 0.0f;
         }
         {   // fc2 B: (kk < 3, nt < 2): W2[t = 8nt+g][k = 8kk+2t4+j]
             const int kk = f / 2, nt = f - kk * 2, t = 8 * nt + g, k = 8 * kk + 2 * t4 + j;
-            sm[L.w2f + i] = (t < kT && k < kTok) ? tf32f(w.tw2[t * kTok + k]) : 0.0f;
+            sm[L.w2f + i] = (t < kT && k < kTok) ? rw(w.tw2[t * kTok + k]) : 0.0f;
         }
         if (bwd) {
             {   // dG1 = dYt W2: (kk < 2, nt < 3): W2[t = 8kk+2t4+j][k = 8nt+g]
                 const int kk = f / 3, nt = f - kk * 3, t = 8 * kk + 2 * t4 + j, k = 8 * nt + g;
-                sm[L.w2g + i] = (t < kT && k < kTok) ? tf32f(w.tw2[t * kTok + k]) : 0.0f;
+                sm[L.w2g + i] = (t < kT && k < kTok) ? rw(w.tw2[t * kTok + k]) : 0.0f;
             }
             {   // dN1 = dU1 W1: (kk < 3, nt < 2): W1[k = 8kk+2t4+j][t = 8nt+g]
                 const int kk = f / 2, nt = f - kk * 2, k = 8 * kk + 2 * t4 + j, t = 8 * nt + g;
-                sm[L.w1g + i] = (k < kTok && t < kT) ? tf32f(w.tw1[k * kT + t]) : 0.0f;
+                sm[L.w1g + i] = (k < kTok && t < kT) ? rw(w.tw1[k * kT + t]) : 0.0f;
             }
         }
     }
@@ -444,6 +505,7 @@ MMX_D void se_rows(const Ctx& cx, const float* pool, const float* dg, float* gat
 
 // ------------------------------------------------------------------------------------------ channel-half building blocks
 // u[mt][nt] = c1' + xhat2 V1'^T      (A from the ns tile, natural K order)
+template <int NX>
 MMX_D void channel_fc1(const Ctx& cx, const float* ns, float (&u)[2][kNT][4]) {
     MMX_UNROLL
     for (int nt = 0; nt < kNT; ++nt) {
@@ -453,47 +515,53 @@ MMX_D void channel_fc1(const Ctx& cx, const float* ns, float (&u)[2][kNT][4]) {
     }
     MMX_UNROLL
     for (int kk = 0; kk < kNT; ++kk) {
-        uint32_t a[2][4];
+        AFrag<NX> a[2];
         MMX_UNROLL
         for (int mt = 0; mt < 2; ++mt) {
             const float* p = ns + (16 * mt + cx.g) * kPA + 8 * kk + cx.t4;
-            a[mt][0] = tf32(p[0]); a[mt][1] = tf32(p[8 * kPA]); a[mt][2] = tf32(p[4]); a[mt][3] = tf32(p[8 * kPA + 4]);
+            prep_a<NX>(p[0], p[8 * kPA], p[4], p[8 * kPA + 4], a[mt]);
         }
         MMX_UNROLL
         for (int nt = 0; nt < kNT; ++nt) {
             const float* q = cx.sm + cx.L.v1 + (8 * nt + cx.g) * kPW + 8 * kk + cx.t4;
-            const uint32_t b0 = __float_as_uint(q[0]), b1 = __float_as_uint(q[4]);
-            mma8(u[0][nt], a[0], b0, b1);
-            mma8(u[1][nt], a[1], b0, b1);
+            BFrag<NX> b;
+            prep_b_w<NX>(q[0], q[4], b);
+            mmaX<NX>(u[0][nt], a[0], b);
+            mmaX<NX>(u[1][nt], a[1], b);
         }
     }
 }
 // out[mt][nt] (+)= in[mt][kk] (chained) * W, with B(k, n) = W[(8nt+g)*kPW + 8kk+2t4 (+1)]     ("NT": W rows are the outputs)
+template <int NX>
 MMX_D void chain_nt(const Ctx& cx, const float* W, const float (&in)[2][kNT][4], float (&out)[2][kNT][4]) {
     MMX_UNROLL
     for (int kk = 0; kk < kNT; ++kk) {
-        uint32_t a[2][4];
-        a_from_c(in[0][kk], a[0]); a_from_c(in[1][kk], a[1]);
+        AFrag<NX> a[2];
+        a_from_c<NX>(in[0][kk], a[0]); a_from_c<NX>(in[1][kk], a[1]);
         MMX_UNROLL
         for (int nt = 0; nt < kNT; ++nt) {
-            const float2 b = *reinterpret_cast<const float2*>(W + (8 * nt + cx.g) * kPW + 8 * kk + 2 * cx.t4);
-            mma8(out[0][nt], a[0], __float_as_uint(b.x), __float_as_uint(b.y));
-            mma8(out[1][nt], a[1], __float_as_uint(b.x), __float_as_uint(b.y));
+            const float2 bv = *reinterpret_cast<const float2*>(W + (8 * nt + cx.g) * kPW + 8 * kk + 2 * cx.t4);
+            BFrag<NX> b;
+            prep_b_w<NX>(bv.x, bv.y, b);
+            mmaX<NX>(out[0][nt], a[0], b);
+            mmaX<NX>(out[1][nt], a[1], b);
         }
     }
 }
 // out[mt][nt] += in[mt][kk] (chained) * W, with B(k, n) = W[(8kk+2t4 (+1))*kPW + 8nt+g]        ("NN": W rows are the contraction)
+template <int NX>
 MMX_D void chain_nn(const Ctx& cx, const float* W, const float (&in)[2][kNT][4], float (&out)[2][kNT][4]) {
     MMX_UNROLL
     for (int kk = 0; kk < kNT; ++kk) {
-        uint32_t a[2][4];
-        a_from_c(in[0][kk], a[0]); a_from_c(in[1][kk], a[1]);
+        AFrag<NX> a[2];
+        a_from_c<NX>(in[0][kk], a[0]); a_from_c<NX>(in[1][kk], a[1]);
         MMX_UNROLL
         for (int nt = 0; nt < kNT; ++nt) {
             const float* q = W + (8 * kk + 2 * cx.t4) * kPW + 8 * nt + cx.g;
-            const uint32_t b0 = __float_as_uint(q[0]), b1 = __float_as_uint(q[kPW]);
-            mma8(out[0][nt], a[0], b0, b1);
-            mma8(out[1][nt], a[1], b0, b1);
+            BFrag<NX> b;
+            prep_b_w<NX>(q[0], q[kPW], b);
+            mmaX<NX>(out[0][nt], a[0], b);
+            mmaX<NX>(out[1][nt], a[1], b);
         }
     }
 }
@@ -527,14 +595,14 @@ MMX_D void rowsum(float (&p)[2][2]) {
 }
 
 // ------------------------------------------------------------------------------------------ forward kernel
-template <int ACT>
+template <int ACT, int NX>
 __global__ void __launch_bounds__(kFwdWarps * 32, 1) mlp_block_fwd_tc_kernel(const MlpBlockFwdArgs a) {
     extern __shared__ float4 mmx_tc_smem_raw[];
     float* sm = reinterpret_cast<float*>(mmx_tc_smem_raw);
     const MlpDims& d = a.d;
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Smem L = smem_layout(false, nwarp);
-    stage(sm, L, d, a.w, false, threadIdx.x, blockDim.x);
+    stage(sm, L, d, a.w, false, NX == 1, threadIdx.x, blockDim.x);
 
     Ctx cx;
     cx.sm = sm; cx.L = L; cx.H = d.H; cx.ch = d.ch; cx.rr = d.rr; cx.use_se = d.use_se; cx.invH = 1.0f / (float)d.H;
@@ -554,7 +622,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) mlp_block_fwd_tc_kernel(con
         MMX_NOUNROLL
         for (int s = 0; s < kSeq; ++s) {
             float x[4][2][4], mu2[4], rs2[4];
-            token_fwd<ACT>(cx, tw, xs, s * kT, (uint32_t)(seq0 + s), x, mu2, rs2);
+            token_fwd<ACT, NX>(cx, tw, xs, s * kT, nullptr, false, (uint32_t)(seq0 + s), x, mu2, rs2);
             scatter_T(xs, s * kT, H, cx.g, cx.t4, x);                                   // X1 (same lane reads / writes each address)
             MMX_UNROLL
             for (int mt = 0; mt < 4; ++mt)
@@ -567,7 +635,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) mlp_block_fwd_tc_kernel(con
         __syncwarp();
         // ---------------- channel half on the group's 32 rows ----------------
         float u[2][kNT][4];
-        channel_fc1(cx, ns, u);
+        channel_fc1<NX>(cx, ns, u);
         {
             uint32_t bits2[2];
             keep_bits<7>(cx.dr, cx.drop, cx.site_base + 2, (uint32_t)grp, lane, bits2);
@@ -585,7 +653,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) mlp_block_fwd_tc_kernel(con
             MMX_UNROLL
             for (int mt = 0; mt < 2; ++mt) { y2[mt][nt][0] = b.x; y2[mt][nt][1] = b.y; y2[mt][nt][2] = b.x; y2[mt][nt][3] = b.y; }
         }
-        chain_nt(cx, sm + L.v2, u, y2);
+        chain_nt<NX>(cx, sm + L.v2, u, y2);
         {
             uint32_t bits3[2];
             keep_bits<7>(cx.dr, cx.drop, cx.site_base + 3, (uint32_t)grp, lane, bits3);
@@ -650,6 +718,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) mlp_block_fwd_tc_kernel(con
 
 // ------------------------------------------------------------------------------------------ backward pieces
 // acc[m][n] += sum_{row < 32} At[row][m] * Bt[row][n]   (m, n < 56; CTA-shared accumulator, one lock per 16 rows of m)
+template <int NX>
 MMX_D void wgrad_rows(float* acc, unsigned int* locks, const float* At, const float* Bt, const Ctx& cx, int warp) {
     MMX_NOUNROLL
     for (int i = 0; i < 4; ++i) {
@@ -660,17 +729,17 @@ MMX_D void wgrad_rows(float* acc, unsigned int* locks, const float* At, const fl
         MMX_UNROLL
         for (int kk = 0; kk < 4; ++kk) {
             const float* pa = At + (8 * kk + cx.t4) * kPA + 16 * mt + cx.g;
-            uint32_t af[4];
-            af[0] = tf32(pa[0]); af[1] = tf32(pa[8]); af[2] = tf32(pa[4 * kPA]); af[3] = tf32(pa[4 * kPA + 8]);
+            AFrag<NX> af;
+            prep_a<NX>(pa[0], pa[8], pa[4 * kPA], pa[4 * kPA + 8], af);
             const float* pb = Bt + (8 * kk + cx.t4) * kPA + cx.g;
             MMX_UNROLL
-            for (int nt = 0; nt < kNT; ++nt) mma8(c[nt], af, tf32(pb[8 * nt]), tf32(pb[4 * kPA + 8 * nt]));
+            for (int nt = 0; nt < kNT; ++nt) { BFrag<NX> b; prep_b_a<NX>(pb[8 * nt], pb[4 * kPA + 8 * nt], b); mmaX<NX>(c[nt], af, b); }
         }
         warp_lock(locks + mt, cx.lane);
         MMX_UNROLL
         for (int hi = 0; hi < 2; ++hi) {
             const int row = 16 * mt + cx.g + 8 * hi;
-            if (row < kHP) {
+            if (row < kAccRows) {
                 MMX_UNROLL
                 for (int nt = 0; nt < kNT; ++nt) {
                     float2* p = reinterpret_cast<float2*>(acc + row * kPAcc + 8 * nt + 2 * cx.t4);
@@ -685,15 +754,16 @@ MMX_D void wgrad_rows(float* acc, unsigned int* locks, const float* At, const fl
 }
 
 // acc[nt] += sum_{h < 64} A[h][m = t] * B[h][n = k]   (token weight gradients; operand tiles [64][kPT])
+template <int NX>
 MMX_D void wgrad_tok(float (&acc)[3][4], const float* A, const float* Bm, const Ctx& cx) {
     MMX_UNROLL
     for (int kk = 0; kk < 8; ++kk) {
         const float* pa = A + (8 * kk + cx.t4) * kPT + cx.g;
-        uint32_t af[4];
-        af[0] = tf32(pa[0]); af[1] = tf32(pa[8]); af[2] = tf32(pa[4 * kPT]); af[3] = tf32(pa[4 * kPT + 8]);
+        AFrag<NX> af;
+        prep_a<NX>(pa[0], pa[8], pa[4 * kPT], pa[4 * kPT + 8], af);
         const float* pb = Bm + (8 * kk + cx.t4) * kPT + cx.g;
         MMX_UNROLL
-        for (int nt = 0; nt < 3; ++nt) mma8(acc[nt], af, tf32(pb[8 * nt]), tf32(pb[4 * kPT + 8 * nt]));
+        for (int nt = 0; nt < 3; ++nt) { BFrag<NX> b; prep_b_a<NX>(pb[8 * nt], pb[4 * kPT + 8 * nt], b); mmaX<NX>(acc[nt], af, b); }
     }
 }
 // token tile [h][k or t] (C layout, NT n8 tiles) -> shared [64][kPT]; optional ones column
@@ -712,14 +782,14 @@ MMX_D void store_tok(float* buf, const Ctx& cx, int mt, const float (&v)[NTL][4]
 }
 
 // ------------------------------------------------------------------------------------------ backward kernel
-template <int ACT>
+template <int ACT, int NX>
 __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(const MlpBlockBwdArgs a) {
     extern __shared__ float4 mmx_tc_smem_raw[];
     float* sm = reinterpret_cast<float*>(mmx_tc_smem_raw);
     const MlpDims& d = a.d;
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Smem L = smem_layout(true, nwarp);
-    stage(sm, L, d, a.w, true, threadIdx.x, blockDim.x);
+    stage(sm, L, d, a.w, true, NX == 1, threadIdx.x, blockDim.x);
 
     Ctx cx;
     cx.sm = sm; cx.L = L; cx.H = d.H; cx.ch = d.ch; cx.rr = d.rr; cx.use_se = d.use_se; cx.invH = 1.0f / (float)d.H;
@@ -727,9 +797,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
     cx.dr = resolve_dropout(a.dr); cx.drop = d.training && cx.dr.thresh != 0u; cx.site_base = d.site_base;
     const int H = d.H, ch = d.ch, g = cx.g, t4 = cx.t4;
     float* ws = sm + L.warp0 + warp * L.wstride;
-    float* xs = ws + L.xs; float* ns = ws + L.ns; float* gs = ws + L.gs; float* ds = ws + L.ds;
-    float* pools = ws + L.pool; float* gates = ws + L.gate; float* dshs = ws + L.dsh; float* dgs = ws + L.dgs; float* rs2s = ws + L.rs2;
-    float* wse = ws + L.wse; float* wln1 = ws + L.wln1;
+    float* ns = ws + L.ns; float* gs = ws + L.gs; float* ds = ws + L.ds;
+    float* pools = ws + L.pool; float* gates = ws + L.gate; float* dshs = ws + L.dsh; float* rs2s = ws + L.rs2;
+    float* wse = ws + L.wse; float* wln1 = sm + L.wln1;      // LN1 weight gradients: CTA-shared, under locks[8]
     unsigned int* locks = reinterpret_cast<unsigned int*>(sm + L.locks);
     if (!d.use_se) { gates[lane] = lane < kSeq * kT ? 1.0f : 0.0f; }      // dsh stays 0
     TokW tw;
@@ -745,13 +815,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
     MMX_NOUNROLL
     for (int grp = blockIdx.x * nwarp + warp; grp < groups; grp += gridDim.x * nwarp) {
         const int seq0 = grp * kSeq, nseq = imin(kSeq, d.B - seq0);
-        load_group(xs, a.x + (size_t)seq0 * kT * H, nseq * kT * H, H, lane);
-        __syncwarp();
         // ---------------- A: token half forward -> xhat2 (ns), rstd2 ----------------
         MMX_NOUNROLL
         for (int s = 0; s < kSeq; ++s) {
             float x[4][2][4], mu2[4], rs2[4];
-            token_fwd<ACT>(cx, tw, xs, s * kT, (uint32_t)(seq0 + s), x, mu2, rs2);
+            token_fwd<ACT, NX>(cx, tw, nullptr, 0, s < nseq ? a.x + (size_t)(seq0 + s) * kT * H : nullptr, true, (uint32_t)(seq0 + s), x, mu2, rs2);
             MMX_UNROLL
             for (int mt = 0; mt < 4; ++mt)
                 MMX_UNROLL
@@ -769,7 +837,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
         // ---------------- B: channel half forward + backward ----------------
         const float* dyg = a.dy + (size_t)seq0 * kT * H;
         float u2[2][kNT][4];
-        channel_fc1(cx, ns, u2);
+        channel_fc1<NX>(cx, ns, u2);
         uint32_t bits2[2], bits3[2];
         keep_bits<7>(cx.dr, cx.drop, cx.site_base + 2, (uint32_t)grp, lane, bits2);
         keep_bits<7>(cx.dr, cx.drop, cx.site_base + 3, (uint32_t)grp, lane, bits3);
@@ -791,7 +859,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                 MMX_UNROLL
                 for (int mt = 0; mt < 2; ++mt) { y2[mt][nt][0] = b.x; y2[mt][nt][1] = b.y; y2[mt][nt][2] = b.x; y2[mt][nt][3] = b.y; }
             }
-            chain_nt(cx, sm + L.v2, g2, y2);
+            chain_nt<NX>(cx, sm + L.v2, g2, y2);
             float p1[2][2], p2[2][2];
             MMX_UNROLL
             for (int mt = 0; mt < 2; ++mt)
@@ -818,11 +886,12 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                     MMX_UNROLL
                     for (int mt = 0; mt < 2; ++mt)
                         MMX_UNROLL
-                        for (int hi = 0; hi < 2; ++hi) { pools[16 * mt + g + 8 * hi] = p1[mt][hi] * cx.invH; dgs[16 * mt + g + 8 * hi] = p2[mt][hi]; }
+                        for (int hi = 0; hi < 2; ++hi) { pools[16 * mt + g + 8 * hi] = p1[mt][hi] * cx.invH; dshs[16 * mt + g + 8 * hi] = p2[mt][hi]; }
                 }
                 __syncwarp();
                 if (lane < kSeq)
-                    se_rows<true>(cx, pools + lane * kT, dgs + lane * kT, gates + lane * kT, dshs + lane * kT, seq0 + lane < d.B, wse + lane * 2 * kMaxRR * kT);
+                    se_rows<true>(cx, pools + lane * kT, dshs + lane * kT, gates + lane * kT, dshs + lane * kT,      // dg in, d pool / H out (in place)
+                                  seq0 + lane < d.B, wse + lane * 2 * kMaxRR * kT);
                 __syncwarp();
             }
             MMX_UNROLL
@@ -847,9 +916,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
         for (int mt = 0; mt < 2; ++mt)
             MMX_UNROLL
             for (int nt = 0; nt < kNT; ++nt) { dg2[mt][nt][0] = dg2[mt][nt][1] = dg2[mt][nt][2] = dg2[mt][nt][3] = 0.0f; }
-        chain_nn(cx, sm + L.v2, dO, dg2);                 // dG2 = dY2 V2
+        chain_nn<NX>(cx, sm + L.v2, dO, dg2);                 // dG2 = dY2 V2
         __syncwarp();
-        wgrad_rows(sm + L.accV2, locks + 0, ds, gs, cx, warp);        // dV2[h][c] += dY2^T G2
+        wgrad_rows<NX>(sm + L.accV2, locks + 0, ds, gs, cx, warp);        // dV2[h][c] += dY2^T G2
         // dU2 = dG2 * mask2 * act'(U2)   (in dg2)
         MMX_UNROLL
         for (int mt = 0; mt < 2; ++mt)
@@ -868,9 +937,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
         for (int mt = 0; mt < 2; ++mt)
             MMX_UNROLL
             for (int nt = 0; nt < kNT; ++nt) { dxh[mt][nt][0] = dxh[mt][nt][1] = dxh[mt][nt][2] = dxh[mt][nt][3] = 0.0f; }
-        chain_nn(cx, sm + L.v1, dg2, dxh);                // d xhat2 = dU2 V1'
+        chain_nn<NX>(cx, sm + L.v1, dg2, dxh);                // d xhat2 = dU2 V1'
         __syncwarp();
-        wgrad_rows(sm + L.accV1, locks + 4, ds, ns, cx, warp);        // W~[c][h] += dU2^T xhat2
+        wgrad_rows<NX>(sm + L.accV1, locks + 4, ds, ns, cx, warp);        // W~[c][h] += dU2^T xhat2
         // LN2 backward: dX1 = dOut + rstd2 * (dxh - mean(dxh) - xhat2 * mean(dxh * xhat2))  -> gs
         {
             float m1[2][2], m2[2][2];
@@ -922,16 +991,16 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
         MMX_NOUNROLL
         for (int s = 0; s < kSeq; ++s) {
             const int rb = s * kT;
-            const uint32_t seq = (uint32_t)(seq0 + s);
             const bool live = seq0 + s < d.B;
             float mu1[4], rs1[4];
             float u1[4][3][4], y[4][2][4];
+            const float* xseq = live ? a.x + (size_t)(seq0 + s) * kT * H : nullptr;
             uint32_t bits0[2], bits1[1];
-            keep_bits<6>(cx.dr, cx.drop, cx.site_base + 0, seq, lane, bits0);
-            keep_bits<4>(cx.dr, cx.drop, cx.site_base + 1, seq, lane, bits1);
+            keep_bits<6>(cx.dr, cx.drop, cx.site_base + 0, (uint32_t)(seq0 + s), lane, bits0);
+            keep_bits<4>(cx.dr, cx.drop, cx.site_base + 1, (uint32_t)(seq0 + s), lane, bits1);
             {
                 float x[4][2][4];
-                load_xT(xs, rb, H, g, t4, x);
+                load_xT_global(xseq, H, g, t4, x);
                 col_stats(x, H, cx.invH, g, mu1, rs1);
                 MMX_UNROLL
                 for (int mt = 0; mt < 4; ++mt) {
@@ -940,14 +1009,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                     for (int nt = 0; nt < 2; ++nt)
                         MMX_UNROLL
                         for (int r = 0; r < 4; ++r) { const int c = nt * 2 + (r & 1); xh[nt][r] = (x[mt][nt][r] - mu1[c]) * rs1[c]; }
-                    token_fc1(cx, tw, xh, mt, u1[mt]);
+                    token_fc1<NX>(cx, tw, xh, mt, u1[mt]);
                     float gv[3][4];
                     MMX_UNROLL
                     for (int nt = 0; nt < 3; ++nt)
                         MMX_UNROLL
                         for (int r = 0; r < 4; ++r) gv[nt][r] = act_fwd<ACT>(u1[mt][nt][r]) * keepf(bits0, mt * 12 + nt * 4 + r, cx.dr.scale);
                     store_tok<3>(bufA, cx, mt, gv, kTok);
-                    token_fc2(tw, gv, y[mt]);
+                    token_fc2<NX>(tw, gv, y[mt]);
                     MMX_UNROLL
                     for (int nt = 0; nt < 2; ++nt)
                         MMX_UNROLL
@@ -1014,24 +1083,24 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
             MMX_UNROLL
             for (int mt = 0; mt < 4; ++mt) store_tok<2>(bufB, cx, mt, y[mt], -1);
             __syncwarp();
-            wgrad_tok(aW2, bufB, bufA, cx);               // dW2[t][k] += dYt^T G1 ; column 20 = db2
+            wgrad_tok<NX>(aW2, bufB, bufA, cx);               // dW2[t][k] += dYt^T G1 ; column 20 = db2
             // pass 2: dG1, dU1, dN1
             float dn[4][2][4];
             {
-                uint32_t w2g[2][3][2], w1g[3][2][2];
+                float w2g[2][3][2], w1g[3][2][2];
                 MMX_UNROLL
                 for (int kk = 0; kk < 2; ++kk)
                     MMX_UNROLL
                     for (int nt = 0; nt < 3; ++nt) {
                         const float2 v = *reinterpret_cast<const float2*>(sm + L.w2g + (kk * 3 + nt) * 64 + lane * 2);
-                        w2g[kk][nt][0] = __float_as_uint(v.x); w2g[kk][nt][1] = __float_as_uint(v.y);
+                        w2g[kk][nt][0] = v.x; w2g[kk][nt][1] = v.y;
                     }
                 MMX_UNROLL
                 for (int kk = 0; kk < 3; ++kk)
                     MMX_UNROLL
                     for (int nt = 0; nt < 2; ++nt) {
                         const float2 v = *reinterpret_cast<const float2*>(sm + L.w1g + (kk * 2 + nt) * 64 + lane * 2);
-                        w1g[kk][nt][0] = __float_as_uint(v.x); w1g[kk][nt][1] = __float_as_uint(v.y);
+                        w1g[kk][nt][0] = v.x; w1g[kk][nt][1] = v.y;
                     }
                 MMX_UNROLL
                 for (int mt = 0; mt < 4; ++mt) {
@@ -1040,10 +1109,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                     for (int nt = 0; nt < 3; ++nt) { dg1[nt][0] = dg1[nt][1] = dg1[nt][2] = dg1[nt][3] = 0.0f; }
                     MMX_UNROLL
                     for (int kk = 0; kk < 2; ++kk) {
-                        uint32_t af[4];
-                        a_from_c(y[mt][kk], af);
+                        AFrag<NX> af;
+                        a_from_c<NX>(y[mt][kk], af);
                         MMX_UNROLL
-                        for (int nt = 0; nt < 3; ++nt) mma8(dg1[nt], af, w2g[kk][nt][0], w2g[kk][nt][1]);
+                        for (int nt = 0; nt < 3; ++nt) { BFrag<NX> b; prep_b_w<NX>(w2g[kk][nt][0], w2g[kk][nt][1], b); mmaX<NX>(dg1[nt], af, b); }
                     }
                     MMX_UNROLL
                     for (int nt = 0; nt < 3; ++nt)
@@ -1057,16 +1126,16 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                     for (int nt = 0; nt < 2; ++nt) { dn[mt][nt][0] = dn[mt][nt][1] = dn[mt][nt][2] = dn[mt][nt][3] = 0.0f; }
                     MMX_UNROLL
                     for (int kk = 0; kk < 3; ++kk) {
-                        uint32_t af[4];
-                        a_from_c(u1[mt][kk], af);
+                        AFrag<NX> af;
+                        a_from_c<NX>(u1[mt][kk], af);
                         MMX_UNROLL
-                        for (int nt = 0; nt < 2; ++nt) mma8(dn[mt][nt], af, w1g[kk][nt][0], w1g[kk][nt][1]);
+                        for (int nt = 0; nt < 2; ++nt) { BFrag<NX> b; prep_b_w<NX>(w1g[kk][nt][0], w1g[kk][nt][1], b); mmaX<NX>(dn[mt][nt], af, b); }
                     }
                 }
             }
             __syncwarp();                                 // the dW2 MMAs have read bufA / bufB
             float xh[4][2][4];
-            load_xT(xs, rb, H, g, t4, xh);
+            load_xT_global(xseq, H, g, t4, xh);
             MMX_UNROLL
             for (int mt = 0; mt < 4; ++mt) {
                 store_tok<3>(bufA, cx, mt, u1[mt], -1);   // dU1
@@ -1085,7 +1154,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                 store_tok<2>(bufB, cx, mt, n1, kT);       // N1 (+ ones at t = 10: dW1^T[10][k] = db1[k])
             }
             __syncwarp();
-            wgrad_tok(aW1, bufB, bufA, cx);               // dW1^T[t][k] += N1^T dU1
+            wgrad_tok<NX>(aW1, bufB, bufA, cx);               // dW1^T[t][k] += N1^T dU1
             // LN1 backward
             {
                 float dxv[4][2][4], q[4][2][4], m1[4], m2[4];
@@ -1125,11 +1194,17 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
         for (int mt = 0; mt < 4; ++mt)
             MMX_UNROLL
             for (int hi = 0; hi < 2; ++hi) {
-                float a1 = gsum[mt][hi], a2 = bsum[mt][hi];
-                a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-                a2 += __shfl_xor_sync(0xffffffffu, a2, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
-                if (t4 == 0) { wln1[16 * mt + g + 8 * hi] += a1; wln1[64 + 16 * mt + g + 8 * hi] += a2; }
+                gsum[mt][hi] += __shfl_xor_sync(0xffffffffu, gsum[mt][hi], 1); gsum[mt][hi] += __shfl_xor_sync(0xffffffffu, gsum[mt][hi], 2);
+                bsum[mt][hi] += __shfl_xor_sync(0xffffffffu, bsum[mt][hi], 1); bsum[mt][hi] += __shfl_xor_sync(0xffffffffu, bsum[mt][hi], 2);
             }
+        warp_lock(locks + 8, lane);
+        if (t4 == 0) {
+            MMX_UNROLL
+            for (int mt = 0; mt < 4; ++mt)
+                MMX_UNROLL
+                for (int hi = 0; hi < 2; ++hi) { wln1[16 * mt + g + 8 * hi] += gsum[mt][hi]; wln1[64 + 16 * mt + g + 8 * hi] += bsum[mt][hi]; }
+        }
+        warp_unlock(locks + 8, lane);
         {
             float* dxg = a.dx + (size_t)seq0 * kT * H;
             const int nvalid = nseq * kT * H;
@@ -1142,14 +1217,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
     }
 
     // ---------------- flush ----------------
-    {   // per-warp register accumulators -> the warp's xs tile: [2][16][24]
+    {   // per-warp register accumulators -> the warp's ns tile: [2][16][24]
         MMX_UNROLL
         for (int nt = 0; nt < 3; ++nt)
             MMX_UNROLL
             for (int r = 0; r < 4; ++r) {
                 const int row = g + 8 * (r >> 1), col = 8 * nt + 2 * t4 + (r & 1);
-                xs[row * 24 + col] = aW2[nt][r];
-                xs[384 + row * 24 + col] = aW1[nt][r];
+                ns[row * 24 + col] = aW2[nt][r];
+                ns[384 + row * 24 + col] = aW1[nt][r];
             }
     }
     __syncthreads();
@@ -1166,15 +1241,13 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
         float sg = 0.0f, sb = 0.0f;
         for (int c = 0; c < ch; ++c) { const float v = a.w.cw1[c * H + h]; sg = fmaf(v, accV1[c * kPAcc + h], sg); sb = fmaf(v, accV1[c * kPAcc + H], sb); }
         red_add(a.g.ln2_g + h, sg); red_add(a.g.ln2_b + h, sb);
-        float s1 = 0.0f, s2 = 0.0f;
-        for (int w = 0; w < nwarp; ++w) { const float* p = sm + L.warp0 + w * L.wstride + L.wln1; s1 += p[h]; s2 += p[64 + h]; }
-        red_add(a.g.ln1_g + h, s1); red_add(a.g.ln1_b + h, s2);
+        red_add(a.g.ln1_g + h, wln1[h]); red_add(a.g.ln1_b + h, wln1[64 + h]);
     }
     for (int c = tid; c < ch; c += nthr) red_add(a.g.cb1 + c, accV1[c * kPAcc + H]);
     for (int i = tid; i < 2 * 384; i += nthr) {
         const int which = i / 384, j = i - which * 384, t = j / 24, k = j - t * 24;
         float v = 0.0f;
-        for (int w = 0; w < nwarp; ++w) v += sm[L.warp0 + w * L.wstride + L.xs + i];
+        for (int w = 0; w < nwarp; ++w) v += sm[L.warp0 + w * L.wstride + L.ns + i];
         if (which == 0) {
             if (t < kT && k < kTok) red_add(a.g.tw2 + t * kTok + k, v);
             else if (t < kT && k == kTok) red_add(a.g.tb2 + t, v);

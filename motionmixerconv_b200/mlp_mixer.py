@@ -144,6 +144,15 @@ class MlpMixer(nn.Module):
         self.pred_len = pred_len
         self.conv_out = nn.Conv1d(self.seq_len, self.pred_len, 1, stride=1)
 
+    def set_precision(self, precision):
+        """"fp32" (1e-5 parity, default) | "tf32" (tensor-core contractions inside the MixerBlocks, 2e-3 parity) | None
+        (follow ``functional.set_precision``).  Not a reference argument: the constructor signature stays the reference's."""
+        if precision is not None and precision not in F_.L.MMX_PREC:
+            raise ValueError("unknown precision %r" % (precision,))
+        for mb in self.Mixer_Block:
+            mb.precision = precision
+        return self
+
     def forward(self, x):
         """x: [B, seq_len, input_size] -> [B, pred_len, num_classes]  (mlp_mixer.py:306-337)."""
         if x.dim() != 3 or x.shape[1] != self.seq_len or x.shape[2] != self.input_size:
