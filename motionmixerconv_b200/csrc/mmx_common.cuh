@@ -264,6 +264,10 @@ struct WarpExec {
     void phase(F&& f) {
         for (int l = 0; l < 32; ++l) f(l);
     }
+    // CTA-wide re-alignment point: carries no data dependency (the warps of a CTA stay independent), it only keeps them
+    // walking the (instruction-cache-sized) loop body together on the GPU.  Every warp of the CTA must reach it the same
+    // number of times.  Nothing to do in the emulator, which runs the warps one after the other.
+    void align() {}
 };
 struct Exec {
     int nthr, bid, nblk;
@@ -292,6 +296,7 @@ struct WarpExec {
         f((int)(threadIdx.x & 31));
         __syncwarp();
     }
+    __device__ __forceinline__ void align() { __syncthreads(); }
 };
 struct Exec {
     int nthr, bid, nblk;

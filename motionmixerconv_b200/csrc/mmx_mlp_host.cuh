@@ -96,6 +96,14 @@ static inline int plan_mlp_block_warp(const MmxMlpBlockDesc* d, bool bwd, MlpDim
     const int max_warps = di.sms * per_sm * nwarp;
     const int waves = (groups + max_warps - 1) / max_warps;
     const int warps_needed = (groups + waves - 1) / waves;
+    // spread the warps over every CTA slot of the device (fewer warps per CTA) instead of filling fewer CTAs: a warp runs
+    // faster with fewer co-resident warps and the makespan is waves x the per-pair latency either way
+    const int slots = di.sms * per_sm;
+    const int spread = imax(2, imin(nwarp, (warps_needed + slots - 1) / slots));
+    if (spread < nwarp && !env_int("MMX_MLP_NO_SPREAD", 0)) {
+        nwarp = spread;
+        bytes = (size_t)mlp_warp_smem(m, bwd, nwarp).total * 4;
+    }
     *out = m; *smem = bytes; *grid = imax(1, (warps_needed + nwarp - 1) / nwarp); *nwarp_out = nwarp;
     return MMX_OK;
 }

@@ -362,7 +362,13 @@ MMX_D void mlp_block_fwd_warp_body(Exec& ex, const MlpBlockFwdArgs& a) {
         float* ws = sm + L.warp0 + wx.warp * L.wstride;
         float* red = ws + L.red;
         float* tot = ws + L.tot;
-        for (int grp = ex.bid * nwarp + wx.warp; grp < groups; grp += ex.nblk * nwarp) {
+        // every warp of the CTA runs the same number of iterations (a warp without a pair runs a dead one: nothing is stored
+        // or accumulated) and the CTA re-aligns a few times per iteration: the loop body is several times the size of the
+        // instruction caches, and warps that walk it together share each fetched line
+        const int per_iter = ex.nblk * nwarp, n_iter = (groups + per_iter - 1) / per_iter;
+        for (int it = 0; it < n_iter; ++it) {
+            const int grp = it * per_iter + ex.bid * nwarp + wx.warp;
+            wx.align();
             // lane geometry (recomputed inside each sub-phase from `lane`)
 #define MMX_LANE_GEOM                                                                                     \
     ST& st = regs[wx.warp * 32 + lane];                                                                   \
@@ -417,6 +423,7 @@ MMX_D void mlp_block_fwd_warp_body(Exec& ex, const MlpBlockFwdArgs& a) {
             });
             if (d.use_se) wx.phase([&](int lane) { red_sum<TC>(red, tot, lane); });
             // X1 = X + gate1 * Yt ; LN2 statistics
+            wx.align();
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM
                 float gate[TC];
@@ -470,6 +477,7 @@ MMX_D void mlp_block_fwd_warp_body(Exec& ex, const MlpBlockFwdArgs& a) {
                 }
             });
             // G2 = drop(act(N2 V1^T + c1)) -> tile1
+            wx.align();
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM
                 MMX_UNROLL
@@ -490,6 +498,7 @@ MMX_D void mlp_block_fwd_warp_body(Exec& ex, const MlpBlockFwdArgs& a) {
                 }
             });
             // Y2 = drop(G2 V2^T + c2) ; SE2 squeeze
+            wx.align();
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM
                 MMX_UNROLL
@@ -568,7 +577,13 @@ MMX_D void mlp_block_bwd_warp_body(Exec& ex, const MlpBlockBwdArgs& a) {
         float* tot = ws + L.tot;
         float* trb = ws + L.tile[1];     // token phase: 2 transpose buffers [NTR][kTrP] (tiles 1..2 are free by then)
         unsigned int* locks = reinterpret_cast<unsigned int*>(sm + L.lock);
-        for (int grp = ex.bid * nwarp + wx.warp; grp < groups; grp += ex.nblk * nwarp) {
+        // every warp of the CTA runs the same number of iterations (a warp without a pair runs a dead one: nothing is stored
+        // or accumulated) and the CTA re-aligns a few times per iteration: the loop body is several times the size of the
+        // instruction caches, and warps that walk it together share each fetched line
+        const int per_iter = ex.nblk * nwarp, n_iter = (groups + per_iter - 1) / per_iter;
+        for (int it = 0; it < n_iter; ++it) {
+            const int grp = it * per_iter + ex.bid * nwarp + wx.warp;
+            wx.align();
             // ---------------- recompute: LN1, token MLP, SE1, X1, LN2, channel MLP ----------------
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM
@@ -671,6 +686,7 @@ MMX_D void mlp_block_bwd_warp_body(Exec& ex, const MlpBlockBwdArgs& a) {
                     if (4 * q < P) st4(t0 + t * P, make_f4(v[0], v[1], v[2], v[3]));
                 }
             });
+            wx.align();
             wx.phase([&](int lane) {      // U2 -> e (registers), G2 -> tile1
                 MMX_LANE_GEOM
                 MMX_UNROLL
@@ -695,6 +711,7 @@ MMX_D void mlp_block_bwd_warp_body(Exec& ex, const MlpBlockBwdArgs& a) {
                     if (4 * q < P) st4(t1 + t * P, make_f4(v[0], v[1], v[2], v[3]));
                 }
             });
+            wx.align();
             // Y2 ; dOut ; SE2 squeeze + dgate2 partials
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM
@@ -757,6 +774,7 @@ MMX_D void mlp_block_bwd_warp_body(Exec& ex, const MlpBlockBwdArgs& a) {
                         if (j < nvh) ws[L.wv + (s * 6 + 5) * 64 + 4 * q + j] += cs[j];
                 }
             });
+            wx.align();
             // dV2[h][c] += dY2^T G2 ; dG2 = dY2 V2
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM
@@ -768,6 +786,7 @@ MMX_D void mlp_block_bwd_warp_body(Exec& ex, const MlpBlockBwdArgs& a) {
                     for (int j = 0; j < 4; ++j) st.b[t][j] = 0.0f;
                 warp_gemm_nn<TC>(st.b, ws + L.tile[2] + s * TC * P, P, sm + L.v2, L.PC, H, q);
             });
+            wx.align();
             // dU2 = dG2 * mask2 * act'(U2) -> tile1 ; dc1
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM
@@ -795,6 +814,7 @@ MMX_D void mlp_block_bwd_warp_body(Exec& ex, const MlpBlockBwdArgs& a) {
                         if (j < nvc) ws[L.wv + (s * 6 + 4) * 64 + 4 * q + j] += cs[j];
                 }
             });
+            wx.align();
             // dV1[c][h] += dU2^T N2 ; dN2 = dU2 V1 ; LN2 backward partials
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM
@@ -829,6 +849,7 @@ MMX_D void mlp_block_bwd_warp_body(Exec& ex, const MlpBlockBwdArgs& a) {
                 red_write<2 * TC>(red, lane, st.rv);
             });
             wx.phase([&](int lane) { red_sum<2 * TC>(red, tot, lane); });
+            wx.align();
             // dX1 = dOut + LN2'(dN2) -> e ; token half: reload X, LN1, token forward, dgate1 partials
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM
@@ -867,6 +888,7 @@ MMX_D void mlp_block_bwd_warp_body(Exec& ex, const MlpBlockBwdArgs& a) {
                 }
             });
             if (d.use_se) wx.phase([&](int lane) { red_sum<TC>(red, tot, lane); });
+            wx.align();
             // dYt = (dX1*gate1 + ds1/H) * mask1 -> c ; db2 partials ; dX1 stashed in tile0 ; dN1 accumulator (a) zeroed
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM
@@ -907,6 +929,7 @@ MMX_D void mlp_block_bwd_warp_body(Exec& ex, const MlpBlockBwdArgs& a) {
             // hidden columns) are transposed through shared memory: lane v then owns value v of unit k-1
             MMX_NOUNROLL
             for (int k = 0; k <= TOKC; ++k) {
+                if ((k & 3) == 0) wx.align();
                 wx.phase([&](int lane) {
                     MMX_LANE_GEOM
                     if (k == 0 && q == 0 && live) {      // db2[t] (token fc2 bias): totals of the dYt row sums
@@ -966,6 +989,7 @@ MMX_D void mlp_block_bwd_warp_body(Exec& ex, const MlpBlockBwdArgs& a) {
                     }
                 });
             }
+            wx.align();
             // LN1 backward: dX = dX1 + LN1'(dN1)
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM

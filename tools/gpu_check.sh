@@ -12,3 +12,4 @@ python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain_$tag.l
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$tag.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_$tag.log 2>&1
 echo "ncu rc=$?"
+python bench.py --precision tf32 --no-cpu-baseline > gpurun_out/bench_tf32_$tag.json 2>> gpurun_out/bench_$tag.err; cat gpurun_out/bench_tf32_$tag.json
