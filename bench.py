@@ -68,46 +68,61 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms.  The sampler is started before the warm-up (nvidia-smi takes
+    a few hundred ms to produce its first line: longer than a short timed region) and `mark()` brackets the timed region;
+    `stop()` reports the samples that fall inside the marks (all samples, and says so, if none did)."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.marks = index, [], None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
+    def mark(self):
+        self.marks.append(time.time())
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
+        lo, hi = (self.marks[0], self.marks[-1] + 0.03) if len(self.marks) >= 2 else (0.0, float("inf"))
+
+        def collect(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1]))
+                    mx.append(float(r[2]))
+                except (ValueError, IndexError):
+                    continue
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            return sorted(sm), mx, reasons
+
+        inside = [row for row in self.rows if lo <= row[0] <= hi]
+        sm, mx, reasons = collect(inside)
+        window = "timed region"
+        if not sm:
+            sm, mx, reasons = collect(self.rows)
+            window = "warm-up + timed region (no sample fell inside the timed region)"
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def make_data(w, n_batches, seed):
@@ -188,6 +203,8 @@ def run_ours(args, w):
     dev = torch.device("cuda", local)
     pg = None
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     model = MlpMixer(**w["cfg"]) if w["family"] == "mlp" else ConvMixer(**w["cfg"])
@@ -226,10 +243,11 @@ def run_ours(args, w):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident arm (value) ----
-    timed(args.warmup, devd, False)
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
+    timed(args.warmup, devd, False)
+    barrier()
+    sampler.mark()
     t_ms, last_loss = timed(args.steps, devd, False)
     barrier()
     # ---- end-to-end arm: pinned host inputs, H2D inside the region, loss read back every step ----
@@ -237,6 +255,7 @@ def run_ours(args, w):
     barrier()
     t_e2e_ms, _ = timed(args.steps, host, True)
     barrier()
+    sampler.mark()
     clocks = sampler.stop()
     # ---- the other arithmetic mode of the same step (device-resident), for the record ----
     t_alt_ms, alt = 0.0, None
@@ -306,7 +325,8 @@ def run_ours(args, w):
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                ent = json.load(f).get(args.workload)
+                tj = json.load(f)
+                ent = tj.get(args.workload + "_" + prec) or tj.get(args.workload)
             if ent:
                 traffic, traffic_src = ent["bytes"], ent["source"]
         roof = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

@@ -25,7 +25,7 @@ static int tc_dims(const MmxMlpBlockDesc* d, MlpDims* m) {
     if (d->act != MMX_ACT_GELU && d->act != MMX_ACT_MISH) return fail(MMX_E_INVALID, "Unknown activation function type: %d", d->act);
     m->B = d->B; m->T = d->T; m->H = d->H; m->tok = d->tok; m->ch = d->ch; m->rr = d->use_se ? d->se_hidden : 0;
     m->use_se = d->use_se; m->use_max = 0; m->training = d->training; m->site_base = d->block_index * 4;
-    m->S = tc::kSeq; m->w_in_smem = 1;
+    m->S = tc::kSeq; m->w_in_smem = 1; m->align_mask = env_int("MMX_TC_ALIGN_MASK", 2) | (env_int("MMX_TC_ALIGN_MASK_FWD", 8) << 16);   // bwd: bits 0-15, fwd: bits 16+ (measured: one re-alignment per iteration is best)
     return MMX_OK;
 }
 

@@ -34,6 +34,7 @@ static inline int plan_mlp_block(const MmxMlpBlockDesc* d, bool bwd, MlpDims* ou
     MlpDims m;
     m.B = d->B; m.T = d->T; m.H = d->H; m.tok = d->tok; m.ch = d->ch; m.rr = d->use_se ? d->se_hidden : 0;
     m.use_se = d->use_se; m.use_max = d->use_max_pooling; m.training = d->training; m.site_base = d->block_index * 4;
+    m.align_mask = 0;
     const int forced = env_int(bwd ? "MMX_MLP_S_BWD" : "MMX_MLP_S_FWD", 0);
     const int two_cta_budget = (di.max_smem + 1024) / 2 - 1024 - 1024;   // room for 2 CTAs / SM
     const int row_target = bwd ? 96 : 128;
@@ -83,7 +84,7 @@ static inline int plan_mlp_block_warp(const MmxMlpBlockDesc* d, bool bwd, MlpDim
     MlpDims m;
     m.B = d->B; m.T = d->T; m.H = d->H; m.tok = d->tok; m.ch = d->ch; m.rr = d->use_se ? d->se_hidden : 0;
     m.use_se = d->use_se; m.use_max = 0; m.training = d->training; m.site_base = d->block_index * 4;
-    m.S = kSPW; m.w_in_smem = 1;
+    m.S = kSPW; m.w_in_smem = 1; m.align_mask = env_int("MMX_MLP_ALIGN_MASK", 64) | (env_int("MMX_MLP_ALIGN_MASK_FWD", 2) << 16);   // bwd: bits 0-15, fwd: bits 16+
     int nwarp = env_int("MMX_MLP_WARPS", kWarpVariantWarps);
     size_t bytes = 0;
     for (; nwarp >= 2; --nwarp) {      // as many warps per CTA as the shared-memory scratch allows

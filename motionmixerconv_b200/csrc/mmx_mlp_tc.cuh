@@ -614,6 +614,8 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) mlp_block_fwd_tc_kernel(con
     TokW tw;
     load_tokw(cx, tw);
 
+    const int amask = d.align_mask >> 16;
+#define TC_ALIGN(i) do { if (amask >> (i) & 1) __syncthreads(); else __syncwarp(); } while (0)
     const int groups = (d.B + kSeq - 1) / kSeq;
     // Every warp of the CTA runs the same number of iterations (a warp without a group runs a dead one: all loads and
     // stores predicated off) and the CTA re-aligns at the phase boundaries: the loop body is far larger than the
@@ -623,9 +625,9 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) mlp_block_fwd_tc_kernel(con
     for (int it = 0; it < n_iter; ++it) {
         const int grp = it * per_iter + blockIdx.x * nwarp + warp;
         const int seq0 = grp * kSeq, nseq = imax(0, imin(kSeq, d.B - seq0));
-        __syncthreads();
+        TC_ALIGN(0);
         load_group(xs, a.x + (size_t)seq0 * kT * H, nseq * kT * H, H, lane);
-        __syncthreads();
+        TC_ALIGN(1);
         MMX_NOUNROLL
         for (int s = 0; s < kSeq; ++s) {
             float x[4][2][4], mu2[4], rs2[4];
@@ -638,9 +640,9 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) mlp_block_fwd_tc_kernel(con
                     MMX_UNROLL
                     for (int r = 0; r < 4; ++r) { const int c = nt * 2 + (r & 1); x[mt][nt][r] = (x[mt][nt][r] - mu2[c]) * rs2[c]; }
             scatter_T(ns, s * kT, H, cx.g, cx.t4, x);                                   // xhat2
-            __syncthreads();
+            TC_ALIGN(2);
         }
-        __syncthreads();
+        TC_ALIGN(3);
         // ---------------- channel half on the group's 32 rows ----------------
         float u[2][kNT][4];
         channel_fc1<NX>(cx, ns, u);
@@ -691,9 +693,9 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) mlp_block_fwd_tc_kernel(con
                     MMX_UNROLL
                     for (int hi = 0; hi < 2; ++hi) pools[16 * mt + cx.g + 8 * hi] = p[mt][hi] * cx.invH;
             }
-            __syncthreads();
+            TC_ALIGN(4);
             if (lane < kSeq) se_rows<false>(cx, pools + lane * kT, nullptr, gates + lane * kT, nullptr, false, nullptr);
-            __syncthreads();
+            TC_ALIGN(5);
             MMX_UNROLL
             for (int mt = 0; mt < 2; ++mt)
                 MMX_UNROLL
@@ -720,10 +722,11 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) mlp_block_fwd_tc_kernel(con
                     }
                 }
             }
-        __syncthreads();
+        TC_ALIGN(6);
     }
 }
 
+#undef TC_ALIGN
 // ------------------------------------------------------------------------------------------ backward pieces
 // acc[m][n] += sum_{row < 32} At[row][m] * Bt[row][n]   (m, n < 56; CTA-shared accumulator, one lock per 16 rows of m)
 template <int NX>
@@ -817,8 +820,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
     for (int nt = 0; nt < 3; ++nt)
         MMX_UNROLL
         for (int r = 0; r < 4; ++r) { aW2[nt][r] = 0.0f; aW1[nt][r] = 0.0f; }
-    __syncthreads();
+    __syncwarp();
 
+    const int amask = d.align_mask & 0xffff;
+#define TC_ALIGN(i) do { if (amask >> (i) & 1) __syncthreads(); else __syncwarp(); } while (0)
     const int groups = (d.B + kSeq - 1) / kSeq;
     // uniform iteration count + CTA re-alignment at the phase boundaries: see the forward kernel
     const int per_iter = gridDim.x * nwarp, n_iter = (groups + per_iter - 1) / per_iter;
@@ -826,7 +831,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
     for (int it = 0; it < n_iter; ++it) {
         const int grp = it * per_iter + blockIdx.x * nwarp + warp;
         const int seq0 = grp * kSeq, nseq = imax(0, imin(kSeq, d.B - seq0));
-        __syncthreads();
+        TC_ALIGN(1);
         // ---------------- A: token half forward -> xhat2 (ns), rstd2 ----------------
         MMX_NOUNROLL
         for (int s = 0; s < kSeq; ++s) {
@@ -843,10 +848,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                 MMX_UNROLL
                 for (int c = 0; c < 4; ++c) { const int t = col_t(c, t4); if (t < kT) rs2s[s * kT + t] = rs2[c]; }
             }
-            __syncthreads();
+            TC_ALIGN(2);
         }
         ns[lane * kPA + H] = 1.0f;          // column of ones: W~[c][H] = sum_rows dU2[row][c] = dc1
-        __syncthreads();
+        TC_ALIGN(3);
         // ---------------- B: channel half forward + backward ----------------
         const float* dyg = a.dy + (size_t)seq0 * kT * H;
         float u2[2][kNT][4];
@@ -901,11 +906,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                         MMX_UNROLL
                         for (int hi = 0; hi < 2; ++hi) { pools[16 * mt + g + 8 * hi] = p1[mt][hi] * cx.invH; dshs[16 * mt + g + 8 * hi] = p2[mt][hi]; }
                 }
-                __syncthreads();
+                TC_ALIGN(4);
                 if (lane < kSeq)
                     se_rows<true>(cx, pools + lane * kT, dshs + lane * kT, gates + lane * kT, dshs + lane * kT,      // dg in, d pool / H out (in place)
                                   seq0 + lane < d.B, wse + lane * 2 * kMaxRR * kT);
-                __syncthreads();
+                TC_ALIGN(5);
             }
             MMX_UNROLL
             for (int mt = 0; mt < 2; ++mt)
@@ -930,7 +935,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
             MMX_UNROLL
             for (int nt = 0; nt < kNT; ++nt) { dg2[mt][nt][0] = dg2[mt][nt][1] = dg2[mt][nt][2] = dg2[mt][nt][3] = 0.0f; }
         chain_nn<NX>(cx, sm + L.v2, dO, dg2);                 // dG2 = dY2 V2
-        __syncthreads();
+        TC_ALIGN(6);
         wgrad_rows<NX>(sm + L.accV2, locks + 0, ds, gs, cx, warp);        // dV2[h][c] += dY2^T G2
         // dU2 = dG2 * mask2 * act'(U2)   (in dg2)
         MMX_UNROLL
@@ -943,7 +948,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                     const float gp = act_fwd_grad<ACT>(u2[mt][nt][r], &av);
                     dg2[mt][nt][r] = dg2[mt][nt][r] * keepf(bits2, (mt * kNT + nt) * 4 + r, cx.dr.scale) * gp;
                 }
-        __syncthreads();
+        TC_ALIGN(7);
         store_H(ds, cx, dg2, -1);
         float dxh[2][kNT][4];
         MMX_UNROLL
@@ -951,7 +956,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
             MMX_UNROLL
             for (int nt = 0; nt < kNT; ++nt) { dxh[mt][nt][0] = dxh[mt][nt][1] = dxh[mt][nt][2] = dxh[mt][nt][3] = 0.0f; }
         chain_nn<NX>(cx, sm + L.v1, dg2, dxh);                // d xhat2 = dU2 V1'
-        __syncthreads();
+        TC_ALIGN(8);
         wgrad_rows<NX>(sm + L.accV1, locks + 4, ds, ns, cx, warp);        // W~[c][h] += dU2^T xhat2
         // LN2 backward: dX1 = dOut + rstd2 * (dxh - mean(dxh) - xhat2 * mean(dxh * xhat2))  -> gs
         {
@@ -994,7 +999,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                     }
                 }
         }
-        __syncthreads();
+        TC_ALIGN(9);
         // ---------------- C: token half backward, one sequence at a time ----------------
         float gsum[4][2], bsum[4][2];
         MMX_UNROLL
@@ -1095,7 +1100,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
             }
             MMX_UNROLL
             for (int mt = 0; mt < 4; ++mt) store_tok<2>(bufB, cx, mt, y[mt], -1);
-            __syncthreads();
+            TC_ALIGN(10);
             wgrad_tok<NX>(aW2, bufB, bufA, cx);               // dW2[t][k] += dYt^T G1 ; column 20 = db2
             // pass 2: dG1, dU1, dN1
             float dn[4][2][4];
@@ -1146,7 +1151,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                     }
                 }
             }
-            __syncthreads();                                 // the dW2 MMAs have read bufA / bufB
+            TC_ALIGN(11);                                 // the dW2 MMAs have read bufA / bufB
             float xh[4][2][4];
             load_xT_global(xseq, H, g, t4, xh);
             MMX_UNROLL
@@ -1166,7 +1171,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                     }
                 store_tok<2>(bufB, cx, mt, n1, kT);       // N1 (+ ones at t = 10: dW1^T[10][k] = db1[k])
             }
-            __syncthreads();
+            TC_ALIGN(12);
             wgrad_tok<NX>(aW1, bufB, bufA, cx);               // dW1^T[t][k] += N1^T dU1
             // LN1 backward
             {
@@ -1200,7 +1205,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                             }
                         }
             }
-            __syncthreads();                              // bufA / bufB are rewritten by the next sequence; CTA re-alignment
+            TC_ALIGN(13);                              // bufA / bufB are rewritten by the next sequence; CTA re-alignment
         }
         // group epilogue: LN1 weight gradients, dx copy-out
         MMX_UNROLL
@@ -1226,9 +1231,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) mlp_block_bwd_tc_kernel(con
                 *reinterpret_cast<float2*>(dxg + e) = *reinterpret_cast<const float2*>(gs + row * kPA + col);
             }
         }
-        __syncthreads();
+        TC_ALIGN(14);
     }
 
+#undef TC_ALIGN
     // ---------------- flush ----------------
     {   // per-warp register accumulators -> the warp's ns tile: [2][16][24]
         MMX_UNROLL
