@@ -1,5 +1,6 @@
-// MixerBlock forward / backward on the tensor cores (TF32 operands, fp32 accumulation): the 2e-3 "bf16/TF32" mode of
-// the north star, selected with MmxMlpBlockDesc.precision = MMX_PREC_TF32.
+// MixerBlock forward / backward on the tensor cores (TF32 operands, fp32 accumulation): the "bf16/TF32" mode of the north
+// star, selected with MmxMlpBlockDesc.precision = MMX_PREC_TF32 (NX = 1).  The NX = 3 build of the same kernels splits every
+// operand into hi + lo TF32 parts ("3xTF32", fp32-grade results, opt-in for the FP32 mode with MMX_MLP_TC_FP32=1).
 //
 // Reference arithmetic: h36m/mlp_mixer.py:138-164 (MixerBlock.forward), :6-34 (SELayer), :44-96 (MlpBlock).
 //
@@ -8,12 +9,13 @@
 // block's instruction stream; what costs time is everything between the contractions (LayerNorm, Mish, dropout, SE,
 // the residuals).  mma.sync keeps every intermediate in the registers of the warp that produced it -- the accumulator
 // fragment of one contraction IS the A fragment of the next (with the K index permuted on the weight side) -- so a whole
-// block runs with four small shared-memory round trips and no CTA barrier.  A tcgen05 formulation would need 128-row
+// block runs with four small shared-memory round trips and no data dependency between the warps of a CTA.  A tcgen05 formulation would need 128-row
 // tiles staged in shared memory for every A operand and a TMEM -> register load in front of every epilogue.
 //
 // Execution model: one WARP owns a group of 3 sequences (30 rows, padded to two m16 tiles) from load to store.
 //   token half  ("T orientation", rows = hidden column h, cols = frame t): X^T fragments are read from the warp's shared
-//                x tile, LN1 statistics are column sums (register adds + 3 shuffles), token fc1 -> act -> fc2 chain in
+//                x tile (forward) or straight from global memory (backward: three shared tiles per warp instead of four ->
+//                up to 8 warps per SM), LN1 statistics are column sums (register adds + 3 shuffles), token fc1 -> act -> fc2 chain in
 //                registers, SE squeeze / excitation in registers, X1 = X + g*Y, LN2 statistics, xhat2 scattered to shared.
 //   channel half ("H orientation", rows = (sequence, frame), cols = h): A fragments of xhat2 from shared, LN2's affine is
 //                folded into the weights (V1' = V1*gamma2, c1' = c1 + V1 beta2), fc1 -> act -> fc2 chain in registers,
@@ -23,6 +25,10 @@
 //                accumulators under one lock per 16-row slice; bias gradients ride along as a column of ones in the
 //                B operand; dgamma2 / dbeta2 / dV1 are derived from the folded gradient at flush time.  The token
 //                weight gradients (K = h) accumulate in 24 registers per lane for the whole kernel.
+//   scheduling:  one CTA per SM, the warps needed for the batch spread over all SMs; every warp of a CTA runs the same number
+//                of iterations (a warp without a group runs a dead one) and the CTA re-aligns ONCE per iteration
+//                (TC_ALIGN points, swept on the GPU: profiles/r1zc_alignment_sweeps.txt) -- the loop body is ~270 KB of SASS,
+//                warps that walk it together share the instruction-cache lines they fetch.
 //
 // This file is plain CUDA (no host emulator build): the CPU suite cannot execute mma.sync.  GPU parity tests:
 // tests/test_gpu_mlp_tc.py.
