@@ -59,6 +59,28 @@ WORKLOADS = {
 }
 
 
+# stdout carries exactly ONE line (the JSON result): file descriptor 1 is pointed at stderr for the whole run, so that banners
+# printed by native libraries (NCCL's "NCCL version ..." when NCCL_DEBUG is set, ...) cannot precede it
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -154,14 +176,14 @@ def run_reference(args, w):
     dt = time.perf_counter() - t0
     val = Bs * args.steps / dt
     sample = "%d-sequence slice of the %d-sequence batch per step, fp32, torch %s CPU, %d threads" % (Bs, w["B"], torch.__version__, cores)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "train sequences/sec", "value": val, "unit": "sequences/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["name"], "model": w["cfg"], "per_gpu_batch": w["B"]},
         "cpu_baseline": {"value": val, "unit": "sequences/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def cpu_baseline(w, budget_s=15.0):
@@ -370,7 +392,7 @@ def run_ours(args, w):
                                   "ms_per_step": t_alt_ms / args.steps}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(w)
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -387,6 +409,7 @@ def main():
                     help="arithmetic of the MixerBlock contractions (north star: fp32 = 1e-5 parity mode, tf32 = 2e-3 parity mode)")
     ap.add_argument("--no-alt-precision", action="store_true", help="skip the extra timing of the other precision mode")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3)
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
