@@ -45,6 +45,7 @@ int plan_linear(int rows, int K, int N, bool bwd, LinearDims* out, size_t* smem,
             const size_t bytes = (size_t)linear_smem(d, bwd).total * 4;
             if (bytes <= (size_t)budget) {
                 d.R = imin(R, round_up(rows, 4));
+                if (d.R == R && R >= 16) d.R = balanced_tile(rows, R, R / 2, 8, di.sms);
                 const size_t b2 = (size_t)linear_smem(d, bwd).total * 4;
                 const int per_sm = imax(1, imin(8, (int)((di.max_smem + 1024) / (b2 + 1024))));
                 *out = d; *smem = b2; *grid = balanced_grid((rows + d.R - 1) / d.R, di.sms * per_sm);
@@ -71,6 +72,7 @@ int plan_head(const MmxMlpHeadDesc* d, bool bwd, MlpHeadDims* out, size_t* smem,
             const size_t bytes = (size_t)mlp_head_smem(h, bwd).total * 4;
             if (bytes <= (size_t)budget) {
                 h.S = imin(S, d->B);
+                if (forced <= 0 && h.S == S && S >= 2) h.S = balanced_tile(d->B, S, (S + 1) / 2, 1, di.sms);
                 const size_t b2 = (size_t)mlp_head_smem(h, bwd).total * 4;
                 const int per_sm = imax(1, imin(8, (int)((di.max_smem + 1024) / (b2 + 1024))));
                 *out = h; *smem = b2; *grid = balanced_grid((d->B + h.S - 1) / h.S, di.sms * per_sm);

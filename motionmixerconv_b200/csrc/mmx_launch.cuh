@@ -104,6 +104,21 @@ static inline int balanced_grid(int ntiles, int max_ctas) {
     return (ntiles + waves - 1) / waves;
 }
 
+// Tile size in [lo, hi] (multiples of `step`) for a loop over n rows / sequences: CTAs are dealt round-robin to the SMs, so
+// the makespan is (tiles on the busiest SM) x (tile size) -- e.g. 4096 sequences in tiles of 9 give 456 tiles = 4 rounds of
+// 148 SMs at 9 sequences, tiles of 7 give 586 tiles = 4 rounds at 7.  Ties go to the larger tile (better weight reuse).
+static inline int balanced_tile(int n, int hi, int lo, int step, int sms) {
+    if (env_int("MMX_NO_BALANCED_TILE", 0)) return hi;
+    int best = hi;
+    long long best_cost = -1;
+    for (int S = hi; S >= imax(lo, 1); S -= step) {
+        const int tiles = (n + S - 1) / S;
+        const long long cost = (long long)((tiles + sms - 1) / sms) * S;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = S; }
+    }
+    return best;
+}
+
 static inline Dropout make_dropout(const MmxDropout& s, int training) {
     Dropout d;
     d.seed_lo = (uint32_t)(s.seed & 0xffffffffull);

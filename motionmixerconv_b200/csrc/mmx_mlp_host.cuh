@@ -60,6 +60,7 @@ static inline int plan_mlp_block(const MmxMlpBlockDesc* d, bool bwd, MlpDims* ou
     if (bestS[pick]) {
         m.w_in_smem = pick;
         m.S = imin(bestS[pick], d->B);
+        if (forced <= 0 && m.S == bestS[pick] && m.S >= 2) m.S = balanced_tile(d->B, m.S, (m.S + 1) / 2, 1, di.sms);
         const size_t bytes = (size_t)mlp_block_smem(m, bwd).total * 4;
         const int per_sm = imax(1, imin(8, (int)((di.max_smem + 1024) / (bytes + 1024))));
         const int ntiles = (d->B + m.S - 1) / m.S;
