@@ -1,10 +1,13 @@
-// mmx_mlp_block_bwd: fused MixerBlock backward (include/mmx.h).
+// mmx_mlp_block_bwd: fused MixerBlock backward (include/mmx.h) -- the C entry point, plus the gelu / generic-WT1 kernels.
 #define MMX_BWD_ACT mmx::ACT_GELU
-#define MMX_BWD_NAME mmx_mlp_bwd_launch_gelu
-#define MMX_BWD_NS mmx_tu_bwd_gelu
+#define MMX_BWD_NAME mmx_mlp_bwd_launch_gelu_wt1
+#define MMX_BWD_NS mmx_tu_bwd_gelu_wt1
+#define MMX_BWD_PART 0
 #include "mmx_api_mlp_bwd.inl"
 
-int mmx_mlp_bwd_launch_mish(const mmx::MlpBlockBwdArgs& a, int wt1, int grid, size_t smem, void* stream);
+#define MMX_DECL_BWD(name) int name(const mmx::MlpBlockBwdArgs& a, int wt1, int grid, size_t smem, void* stream)
+MMX_DECL_BWD(mmx_mlp_bwd_launch_gelu_wt4); MMX_DECL_BWD(mmx_mlp_bwd_launch_gelu_warp);
+MMX_DECL_BWD(mmx_mlp_bwd_launch_mish_wt1); MMX_DECL_BWD(mmx_mlp_bwd_launch_mish_wt4); MMX_DECL_BWD(mmx_mlp_bwd_launch_mish_warp);
 
 bool mmx_mlp_tc_ok(const MmxMlpBlockDesc* d);
 int mmx_mlp_tc_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads,
@@ -26,6 +29,8 @@ extern "C" int mmx_mlp_block_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockPara
     a.w = to_w(w); a.g = to_w(grads); a.x = x; a.dy = dy; a.dx = dx;
     const int tiles = imax(((d->ch + 3) / 4) * ((d->H + 3) / 4), 1);
     const int wt1 = warp_variant ? -nwarp : (tiles <= kThreads);
-    return d->act == MMX_ACT_GELU ? mmx_mlp_bwd_launch_gelu(a, wt1, grid, smem, stream)
-                                  : mmx_mlp_bwd_launch_mish(a, wt1, grid, smem, stream);
+    const bool gelu = d->act == MMX_ACT_GELU;
+    if (warp_variant) return gelu ? mmx_mlp_bwd_launch_gelu_warp(a, wt1, grid, smem, stream) : mmx_mlp_bwd_launch_mish_warp(a, wt1, grid, smem, stream);
+    if (wt1) return gelu ? mmx_mlp_bwd_launch_gelu_wt1(a, wt1, grid, smem, stream) : mmx_mlp_bwd_launch_mish_wt1(a, wt1, grid, smem, stream);
+    return gelu ? mmx_mlp_bwd_launch_gelu_wt4(a, wt1, grid, smem, stream) : mmx_mlp_bwd_launch_mish_wt4(a, wt1, grid, smem, stream);
 }

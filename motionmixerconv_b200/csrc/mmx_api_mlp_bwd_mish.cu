@@ -1,4 +1,6 @@
+// mmx_mlp_block_bwd, mish activation, generic kernels with one weight-gradient tile per thread (see mmx_api_mlp_bwd.inl).
 #define MMX_BWD_ACT mmx::ACT_MISH
-#define MMX_BWD_NAME mmx_mlp_bwd_launch_mish
-#define MMX_BWD_NS mmx_tu_bwd_mish
+#define MMX_BWD_NAME mmx_mlp_bwd_launch_mish_wt1
+#define MMX_BWD_NS mmx_tu_bwd_mish_wt1
+#define MMX_BWD_PART 0
 #include "mmx_api_mlp_bwd.inl"
