@@ -20,6 +20,9 @@ namespace mmx {
 constexpr int kLPS = 16;   // lanes per sequence
 constexpr int kSPW = 2;    // sequences per warp
 constexpr int kAccP = 64;  // pitch of the swizzled dV accumulators
+constexpr int kRedP = 36;  // row pitch of the per-warp reduction exchange [value][lane]: 4 (mod 32), so the 8 lanes of a
+                           // quarter-warp that read 8 different values' rows with 128-bit loads hit 8 different bank groups
+                           // (pitch 32 made every such load an 8-way conflict: ncu, 35-46 % of the shared wavefronts)
 
 template <int TC>
 struct WLane {
@@ -63,7 +66,7 @@ MMX_HD MlpWarpSmem mlp_warp_smem(const MlpDims& d, bool bwd, int nwarp) {
     int tsz = kSPW * T * L.P;
     if (bwd) tsz = imax(tsz, (2 * T + 1) * kTrP);   // tiles 1..2 double as the two token transpose buffers
     for (int i = 0; i < 3; ++i) L.tile[i] = i < ntile ? wtake(tsz) : -1;
-    L.red = wtake((bwd ? 2 : 1) * T * 32);   // [value][lane]; the backward's transpose buffers (2 x 21 x kTrP) alias tile[1..2]
+    L.red = wtake((bwd ? 2 : 1) * T * kRedP);   // [value][lane]; the backward's transpose buffers (2 x 21 x kTrP) alias tile[1..2]
     L.tot = wtake(kSPW * 2 * T);
     L.mean1 = wtake(kSPW * 16); L.rstd1 = wtake(kSPW * 16); L.pool1 = wtake(kSPW * 16); L.gate1 = wtake(kSPW * 16);
     L.z1 = wtake(kSPW * 16);
@@ -84,13 +87,13 @@ MMX_HD MlpWarpSmem mlp_warp_smem(const MlpDims& d, bool bwd, int nwarp) {
 template <int NR>
 MMX_D void red_write(float* red, int lane, const float* rv) {
     MMX_UNROLL
-    for (int r = 0; r < NR; ++r) red[r * 32 + lane] = rv[r];
+    for (int r = 0; r < NR; ++r) red[r * kRedP + lane] = rv[r];
 }
 template <int NR>
 MMX_D void red_sum(const float* red, float* tot, int lane) {
     for (int i = lane; i < kSPW * NR; i += 32) {
         const int s = i / NR, r = i - s * NR;
-        const float* p = red + r * 32 + s * kLPS;
+        const float* p = red + r * kRedP + s * kLPS;
         const f4 v0 = ld4(p), v1 = ld4(p + 4), v2 = ld4(p + 8), v3 = ld4(p + 12);
         tot[i] = (((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w))) +
                  (((v2.x + v2.y) + (v2.z + v2.w)) + ((v3.x + v3.y) + (v3.z + v3.w)));
