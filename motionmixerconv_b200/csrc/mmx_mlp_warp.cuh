@@ -187,10 +187,11 @@ MMX_D int acc_sw(int r, int c) { return r * kAccP + ((((c >> 2) ^ (((r >> 3) & 7
 
 template <int TC>
 MMX_D void warp_wgrad(float* accm, unsigned int* lock, const float* At, const float* Bt, int P, int RA, int CB, int lane,
-                      bool live0, bool live1) {
+                      bool live0, bool live1, int first) {
     const int lr = lane >> 2, lc = lane & 3, r0 = 8 * lr;
     MMX_NOUNROLL
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pp = 0; pp < 2; ++pp) {
+        const int pass = pp ^ (first & 1);      // odd warps take the column halves (and their locks) in the other order
         const int c0 = 16 * lc + 8 * pass;
         const bool work = r0 < RA && c0 < CB;
         float acc[8][8];
@@ -790,7 +791,7 @@ MMX_D void mlp_block_bwd_warp_body(Exec& ex, const MlpBlockBwdArgs& a) {
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM
                 const bool live0 = (long long)grp * kSPW < d.B, live1 = (long long)grp * kSPW + 1 < d.B;
-                warp_wgrad<TC>(sm + L.a_v2, locks + 2, ws + L.tile[2], ws + L.tile[1], P, H, ch, lane, live0, live1);
+                warp_wgrad<TC>(sm + L.a_v2, locks + 2, ws + L.tile[2], ws + L.tile[1], P, H, ch, lane, live0, live1, wx.warp);
                 MMX_UNROLL
                 for (int t = 0; t < TC; ++t)
                     MMX_UNROLL
@@ -830,7 +831,7 @@ MMX_D void mlp_block_bwd_warp_body(Exec& ex, const MlpBlockBwdArgs& a) {
             wx.phase([&](int lane) {
                 MMX_LANE_GEOM
                 const bool live0 = (long long)grp * kSPW < d.B, live1 = (long long)grp * kSPW + 1 < d.B;
-                warp_wgrad<TC>(sm + L.a_v1, locks + 0, ws + L.tile[1], ws + L.tile[0], P, ch, H, lane, live0, live1);
+                warp_wgrad<TC>(sm + L.a_v1, locks + 0, ws + L.tile[1], ws + L.tile[0], P, ch, H, lane, live0, live1, wx.warp);
                 MMX_UNROLL
                 for (int t = 0; t < TC; ++t)
                     MMX_UNROLL
