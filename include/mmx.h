@@ -32,8 +32,10 @@ extern "C" {
 #define MMX_ACT_MISH 1
 
 /* Arithmetic of the contractions inside a fused block.  FP32: fp32 FMA everywhere (1e-5 parity with the reference).
- * TF32: tensor-core MMAs with TF32-rounded operands and fp32 accumulation (2e-3 parity); LayerNorm, activations, SE,
- * residuals and every reduction stay fp32.  TF32 is a permission: shapes the tensor-core kernels do not serve run FP32. */
+ * TF32 (the reduced-precision "bf16/TF32" mode, 2e-3 parity): the channel-MLP contractions run on the tensor cores --
+ * tcgen05.mma on bf16 operands split hi + lo (three MMAs per product, fp32 accumulation in TMEM) where the tcgen05 family
+ * serves the shape, mma.sync TF32 otherwise; LayerNorm, activations, SE, residuals and every reduction stay fp32.
+ * It is a permission: shapes no tensor-core kernel serves run FP32. */
 #define MMX_PREC_FP32 0
 #define MMX_PREC_TF32 1
 
@@ -81,6 +83,11 @@ int mmx_mlp_block_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, cons
  * dx: [B,T,H] written; grads: accumulated. */
 int mmx_mlp_block_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads,
                       const float* x, const float* dy, float* dx, void* stream);
+
+/* Diagnostics of the tcgen05 / TMEM MixerBlock kernels (precision == MMX_PREC_TF32): number of kernels whose mbarrier waits
+ * timed out since the process started (a mis-programmed pipeline ends the kernel instead of hanging the GPU); 0 in a healthy
+ * run.  Synchronises the device. */
+int mmx_tc5_abort_count(void);
 
 /* y[r,:] = W x[r,:] + b  — MlpMixer.conv (Conv2d(1,H,(1,D)) == per-frame Linear, mlp_mixer.py:268,325-327)
  * and PoseEncoder.embed_mlp without harmonics (positional_encoder.py:91).  x:[rows,K] w:[N,K] y:[rows,N]. */

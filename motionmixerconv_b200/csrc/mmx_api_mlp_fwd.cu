@@ -18,6 +18,8 @@ int dispatch_mlp_fwd(const MlpBlockFwdArgs& a, int grid, size_t smem, void* stre
 }  // namespace mmx_tu_mlp_fwd
 using namespace mmx_tu_mlp_fwd;
 
+bool mmx_mlp_tc5_ok(const MmxMlpBlockDesc* d);
+int mmx_mlp_tc5_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* y, void* stream);
 bool mmx_mlp_tc_ok(const MmxMlpBlockDesc* d);
 int mmx_mlp_tc_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* y, void* stream);
 
@@ -26,6 +28,7 @@ extern "C" int mmx_mlp_block_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockPara
     MlpBlockFwdArgs a;
     size_t smem; int grid, nwarp = 0;
     if (!d) return fail(MMX_E_INVALID, "null descriptor");
+    if (mmx_mlp_tc5_ok(d)) return mmx_mlp_tc5_fwd(d, w, x, y, stream);   // tcgen05 / TMEM family (sm_100a)
     if (mmx_mlp_tc_ok(d)) return mmx_mlp_tc_fwd(d, w, x, y, stream);
     const bool warp_variant = mlp_warp_variant_ok(d);
     int rc = warp_variant ? plan_mlp_block_warp(d, false, &a.d, &smem, &grid, &nwarp) : plan_mlp_block(d, false, &a.d, &smem, &grid);

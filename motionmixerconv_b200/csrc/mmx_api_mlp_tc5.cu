@@ -1,0 +1,229 @@
+// MixerBlock on the Blackwell tensor cores: launch layer of the tcgen05 kernel family (mmx_tok.cuh + mmx_chan_tc5.cuh).
+// Reached from mmx_mlp_block_fwd / mmx_mlp_block_bwd when MmxMlpBlockDesc.precision == MMX_PREC_TF32 (the reduced-precision,
+// 2e-3 mode) and the shape is one this family serves.  A block runs as
+//     forward :  token half (x -> x1, written into y)            ->  channel half (y -> y, in place, tile-local)
+//     backward:  token half forward (x -> x1, written into dx)   ->  channel half backward (dx = x1, dy -> dx = dx1, in place)
+//                                                                ->  token half backward (x, dx = dx1 -> dx, in place)
+// so no workspace is needed beyond the caller's output buffer.
+#include "mmx_launch.cuh"
+
+#if defined(MMX_HOST_EMU)
+bool mmx_mlp_tc5_ok(const MmxMlpBlockDesc*) { return false; }
+int mmx_mlp_tc5_fwd(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, const float*, float*, void*) { return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator"); }
+int mmx_mlp_tc5_bwd(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, const MmxMlpBlockParams*, const float*, const float*, float*, void*) {
+    return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator");
+}
+extern "C" int mmx_tc5_abort_count(void) { return 0; }
+#else
+#include <mutex>
+
+#include "mmx_chan_tc5.cuh"
+#include "mmx_tok.cuh"
+
+using namespace mmx;
+
+__device__ int g_mmx_tc5_abort = 0;
+
+static int* abort_ptr() {
+    static int* p[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!p[dev]) {
+        void* q = nullptr;
+        cudaGetSymbolAddress(&q, g_mmx_tc5_abort);
+        p[dev] = (int*)q;
+    }
+    return p[dev];
+}
+
+// number of kernels of this family whose pipeline waits timed out since the process started (0 in a healthy run); synchronises
+extern "C" int mmx_tc5_abort_count(void) {
+    int v = 0;
+    cudaMemcpy(&v, abort_ptr(), sizeof(int), cudaMemcpyDeviceToHost);
+    return v;
+}
+
+static int kp_of(const MmxMlpBlockDesc* d) {
+    const int need = (d->H > d->ch ? d->H : d->ch) + 1;      // + the ones column that carries the bias gradients
+    return need <= 64 ? 64 : (need <= 80 ? 80 : 0);
+}
+
+bool mmx_mlp_tc5_ok(const MmxMlpBlockDesc* d) {
+    if (d->precision != MMX_PREC_TF32 || env_int("MMX_MLP_NO_TC5", 0)) return false;
+    if (d->T < 2 || d->T > tok::kMaxT || d->tok < 1 || d->tok > tok::kMaxTok) return false;
+    if (d->H < 8 || d->ch < 8 || (d->H & 1) || kp_of(d) == 0) return false;
+    if ((d->T * d->H) & 3) return false;                      // bulk copies: every tile is a multiple of 16 bytes
+    if (d->use_max_pooling) return false;
+    if (d->use_se && (d->se_hidden < 1 || d->se_hidden > chan::kMaxRR)) return false;
+    if (d->H > 512) return false;
+    return true;
+}
+
+template <class K, class A>
+static int launch_tc5(K kern, const A& a, int grid, int block, size_t smem, void* stream) {
+    struct Conf { const void* fn; int dev; size_t smem; };
+    static Conf conf[128];
+    static int nconf = 0;
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        int slot = -1;
+        for (int i = 0; i < nconf; ++i)
+            if (conf[i].fn == (const void*)kern && conf[i].dev == dev) slot = i;
+        if (slot < 0 || conf[slot].smem < smem) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail(MMX_E_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+            if (slot < 0 && nconf < 128) slot = nconf++;
+            if (slot >= 0) conf[slot] = Conf{(const void*)kern, dev, smem};
+        }
+    }
+    kern<<<grid, block, smem, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(MMX_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+    return MMX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ token half
+static int tok_S(const MmxMlpBlockDesc* d, int* nw) {
+    int S = 256 / d->H;
+    if (S < 1) S = 1;
+    while (S > 1 && ((S * d->T * d->H) & 3)) --S;
+    int need = S * d->H;
+    if (S * d->T > need) need = S * d->T;
+    *nw = need <= 256 ? 8 : 16;
+    return S;
+}
+
+static void fill_tok(tok::TokArgs& t, const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* g, int S) {
+    t.ln_g = w->ln1_w; t.ln_b = w->ln1_b; t.w1 = w->tok_w1; t.b1 = w->tok_b1; t.w2 = w->tok_w2; t.b2 = w->tok_b2;
+    t.se1 = w->se_w1; t.se2 = w->se_w2;
+    if (g) {
+        t.g_ln_g = g->ln1_w; t.g_ln_b = g->ln1_b; t.g_w1 = g->tok_w1; t.g_b1 = g->tok_b1; t.g_w2 = g->tok_w2; t.g_b2 = g->tok_b2;
+        t.g_se1 = g->se_w1; t.g_se2 = g->se_w2;
+    } else {
+        t.g_ln_g = t.g_ln_b = t.g_w1 = t.g_b1 = t.g_w2 = t.g_b2 = t.g_se1 = t.g_se2 = nullptr;
+    }
+    t.B = d->B; t.T = d->T; t.H = d->H; t.tok = d->tok; t.rr = d->use_se ? d->se_hidden : 0;
+    t.S = S; t.site_base = d->block_index * 4;
+    t.dr = make_dropout(d->dropout, d->training);
+    t.abort_count = abort_ptr();
+}
+
+template <int ACT, int TT>
+static int run_tok(bool bwd, const tok::TokArgs& t, int nw, void* stream) {
+    const DevInfo di = dev_info();
+    const tok::TokSmem m = tok::tok_smem(t.T, t.H, t.tok, t.S, bwd);
+    const size_t smem = (size_t)m.total * 4;
+    if (smem > (size_t)di.max_smem) return fail(MMX_E_UNSUPPORTED, "token half: tile does not fit shared memory (H=%d)", t.H);
+    const int threads = nw * 32;
+    int per_sm = (int)((di.max_smem + 1024) / (smem + 1024));
+    per_sm = imax(1, imin(per_sm, 2048 / threads));
+    const int ntiles = (t.B + t.S - 1) / t.S;
+    const int grid = balanced_grid(ntiles, di.sms * per_sm);
+    if (nw == 8) return bwd ? launch_tc5(tok::tok_bwd_kernel<ACT, TT, 8>, t, grid, threads, smem, stream)
+                            : launch_tc5(tok::tok_fwd_kernel<ACT, TT, 8>, t, grid, threads, smem, stream);
+    return bwd ? launch_tc5(tok::tok_bwd_kernel<ACT, TT, 16>, t, grid, threads, smem, stream)
+               : launch_tc5(tok::tok_fwd_kernel<ACT, TT, 16>, t, grid, threads, smem, stream);
+}
+
+static int tok_dispatch(bool bwd, const MmxMlpBlockDesc* d, const tok::TokArgs& t, int nw, void* stream) {
+    const bool gelu = d->act == MMX_ACT_GELU;
+    if (d->T == 10) return gelu ? run_tok<ACT_GELU, 10>(bwd, t, nw, stream) : run_tok<ACT_MISH, 10>(bwd, t, nw, stream);
+    return gelu ? run_tok<ACT_GELU, 16>(bwd, t, nw, stream) : run_tok<ACT_MISH, 16>(bwd, t, nw, stream);
+}
+
+// ------------------------------------------------------------------------------------------ channel half
+static void fill_chan(chan::ChanArgs& c, const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* g) {
+    c.ln_g = w->ln2_w; c.ln_b = w->ln2_b; c.w1 = w->ch_w1; c.b1 = w->ch_b1; c.w2 = w->ch_w2; c.b2 = w->ch_b2;
+    c.se1 = w->se_w1; c.se2 = w->se_w2;
+    if (g) {
+        c.g_ln_g = g->ln2_w; c.g_ln_b = g->ln2_b; c.g_w1 = g->ch_w1; c.g_b1 = g->ch_b1; c.g_w2 = g->ch_w2; c.g_b2 = g->ch_b2;
+        c.g_se1 = g->se_w1; c.g_se2 = g->se_w2;
+    } else {
+        c.g_ln_g = c.g_ln_b = c.g_w1 = c.g_b1 = c.g_w2 = c.g_b2 = c.g_se1 = c.g_se2 = nullptr;
+    }
+    c.B = d->B; c.T = d->T; c.H = d->H; c.ch = d->ch; c.rr = d->use_se ? d->se_hidden : 0;
+    c.site_base = d->block_index * 4;
+    c.dr = make_dropout(d->dropout, d->training);
+    c.abort_count = abort_ptr();
+}
+
+template <int ACT, int KP, int VEC>
+static int run_chan(bool bwd, const chan::ChanArgs& c, void* stream) {
+    const DevInfo di = dev_info();
+    const size_t smem = chan::chan_smem_bytes<KP>(c.T, c.H, VEC, bwd);
+    if (smem > (size_t)di.max_smem) return fail(MMX_E_UNSUPPORTED, "channel half: tile does not fit shared memory (H=%d ch=%d)", c.H, c.ch);
+    const chan::Geo g = chan::make_geo(c.T, c.H, VEC);
+    const int ntiles = (c.B + g.seq_per_tile - 1) / g.seq_per_tile;
+    // TMEM: forward 2*KP columns (<= 2 CTAs / SM at KP = 64), backward 4*KP columns
+    int per_sm = (int)((di.max_smem + 1024) / (smem + 1024));
+    const int tm_cols = bwd ? (4 * KP <= 256 ? 256 : 512) : (2 * KP <= 128 ? 128 : (2 * KP <= 256 ? 256 : 512));
+    per_sm = imax(1, imin(per_sm, 512 / tm_cols));
+    const int grid = imin(ntiles, di.sms * per_sm);
+    return bwd ? launch_tc5(chan::chan_bwd_kernel<ACT, KP, VEC>, c, grid, chan::kThreadsChan, smem, stream)
+               : launch_tc5(chan::chan_fwd_kernel<ACT, KP, VEC>, c, grid, chan::kThreadsChan, smem, stream);
+}
+
+template <int ACT>
+static int chan_dispatch_act(bool bwd, const MmxMlpBlockDesc* d, const chan::ChanArgs& c, void* stream) {
+    const int kp = kp_of(d);
+    const bool vec4 = (d->H & 3) == 0;
+    if (kp == 64) return vec4 ? run_chan<ACT, 64, 4>(bwd, c, stream) : run_chan<ACT, 64, 2>(bwd, c, stream);
+    return vec4 ? run_chan<ACT, 80, 4>(bwd, c, stream) : run_chan<ACT, 80, 2>(bwd, c, stream);
+}
+static int chan_dispatch(bool bwd, const MmxMlpBlockDesc* d, const chan::ChanArgs& c, void* stream) {
+    return d->act == MMX_ACT_GELU ? chan_dispatch_act<ACT_GELU>(bwd, d, c, stream) : chan_dispatch_act<ACT_MISH>(bwd, d, c, stream);
+}
+
+static int check_common(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const char* what) {
+    if (d->B <= 0) return fail(MMX_E_INVALID, "non-positive dimension");
+    if (d->act != MMX_ACT_GELU && d->act != MMX_ACT_MISH) return fail(MMX_E_INVALID, "Unknown activation function type: %d", d->act);
+    if (!w) return fail(MMX_E_INVALID, "%s: null parameter table", what);
+    const float* v[] = {w->ln1_w, w->ln1_b, w->tok_w1, w->tok_b1, w->tok_w2, w->tok_b2, w->ln2_w, w->ln2_b, w->ch_w1, w->ch_b1, w->ch_w2, w->ch_b2};
+    for (const float* q : v)
+        if (!q) return fail(MMX_E_INVALID, "%s: null parameter pointer", what);
+    if (d->use_se && (!w->se_w1 || !w->se_w2)) return fail(MMX_E_INVALID, "%s: use_se set but SE weights are null", what);
+    return MMX_OK;
+}
+
+int mmx_mlp_tc5_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* y, void* stream) {
+    int rc = check_common(d, w, "mmx_mlp_block_fwd");
+    if (rc) return rc;
+    if ((((uintptr_t)x) | ((uintptr_t)y)) & 15) return fail(MMX_E_INVALID, "mmx_mlp_block_fwd: tensors must be 16-byte aligned");
+    int nw;
+    const int S = tok_S(d, &nw);
+    tok::TokArgs t;
+    fill_tok(t, d, w, nullptr, S);
+    t.x = x; t.dx1 = nullptr; t.out = y;
+    if ((rc = tok_dispatch(false, d, t, nw, stream))) return rc;
+    chan::ChanArgs c;
+    fill_chan(c, d, w, nullptr);
+    c.x1 = y; c.dy = nullptr; c.out = y;
+    return chan_dispatch(false, d, c, stream);
+}
+
+int mmx_mlp_tc5_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads, const float* x,
+                    const float* dy, float* dx, void* stream) {
+    int rc = check_common(d, w, "mmx_mlp_block_bwd");
+    if (rc) return rc;
+    if ((rc = check_common(d, grads, "mmx_mlp_block_bwd(grads)"))) return rc;
+    if ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dx)) & 15) return fail(MMX_E_INVALID, "mmx_mlp_block_bwd: tensors must be 16-byte aligned");
+    if (dx == dy || dx == x) return fail(MMX_E_INVALID, "mmx_mlp_block_bwd: dx must not alias x or dy");
+    int nw;
+    const int S = tok_S(d, &nw);
+    tok::TokArgs t;
+    fill_tok(t, d, w, grads, S);
+    t.x = x; t.dx1 = nullptr; t.out = dx;                         // x1 -> dx
+    if ((rc = tok_dispatch(false, d, t, nw, stream))) return rc;
+    chan::ChanArgs c;
+    fill_chan(c, d, w, grads);
+    c.x1 = dx; c.dy = dy; c.out = dx;                             // dx1 -> dx (in place)
+    if ((rc = chan_dispatch(true, d, c, stream))) return rc;
+    t.dx1 = dx; t.out = dx;
+    return tok_dispatch(true, d, t, nw, stream);
+}
+#endif
