@@ -56,7 +56,7 @@ bool mmx_mlp_tc5_ok(const MmxMlpBlockDesc* d) {
     if ((d->T * d->H) & 3) return false;                      // bulk copies: every tile is a multiple of 16 bytes
     if (d->use_max_pooling) return false;
     if (d->use_se && (d->se_hidden < 1 || d->se_hidden > chan::kMaxRR)) return false;
-    if (d->H > 512) return false;
+    if (d->H > tok::kTokThreads) return false;
     return true;
 }
 
@@ -88,13 +88,9 @@ static int launch_tc5(K kern, const A& a, int grid, int block, size_t smem, void
 }
 
 // ------------------------------------------------------------------------------------------ token half
-static int tok_S(const MmxMlpBlockDesc* d, int* nw) {
-    int S = 256 / d->H;
+static int tok_S(const MmxMlpBlockDesc* d) {
+    int S = imin(tok::kTokThreads / d->H, tok::kTokThreads / d->T);
     if (S < 1) S = 1;
-    while (S > 1 && ((S * d->T * d->H) & 3)) --S;
-    int need = S * d->H;
-    if (S * d->T > need) need = S * d->T;
-    *nw = need <= 256 ? 8 : 16;
     return S;
 }
 
@@ -114,26 +110,24 @@ static void fill_tok(tok::TokArgs& t, const MmxMlpBlockDesc* d, const MmxMlpBloc
 }
 
 template <int ACT, int TT>
-static int run_tok(bool bwd, const tok::TokArgs& t, int nw, void* stream) {
+static int run_tok(bool bwd, const tok::TokArgs& t, void* stream) {
     const DevInfo di = dev_info();
-    const tok::TokSmem m = tok::tok_smem(t.T, t.H, t.tok, t.S, bwd);
+    const tok::TokSmem m = tok::tok_smem(t.T, t.H, t.tok, t.S, TT, bwd);
     const size_t smem = (size_t)m.total * 4;
     if (smem > (size_t)di.max_smem) return fail(MMX_E_UNSUPPORTED, "token half: tile does not fit shared memory (H=%d)", t.H);
-    const int threads = nw * 32;
+    const int threads = tok::kTokThreads;
     int per_sm = (int)((di.max_smem + 1024) / (smem + 1024));
-    per_sm = imax(1, imin(per_sm, 2048 / threads));
+    per_sm = imax(1, imin(per_sm, env_int("MMX_TOK_CTAS", bwd ? 2 : 4)));
     const int ntiles = (t.B + t.S - 1) / t.S;
     const int grid = balanced_grid(ntiles, di.sms * per_sm);
-    if (nw == 8) return bwd ? launch_tc5(tok::tok_bwd_kernel<ACT, TT, 8>, t, grid, threads, smem, stream)
-                            : launch_tc5(tok::tok_fwd_kernel<ACT, TT, 8>, t, grid, threads, smem, stream);
-    return bwd ? launch_tc5(tok::tok_bwd_kernel<ACT, TT, 16>, t, grid, threads, smem, stream)
-               : launch_tc5(tok::tok_fwd_kernel<ACT, TT, 16>, t, grid, threads, smem, stream);
+    return bwd ? launch_tc5(tok::tok_bwd_kernel<ACT, TT>, t, grid, threads, smem, stream)
+               : launch_tc5(tok::tok_fwd_kernel<ACT, TT>, t, grid, threads, smem, stream);
 }
 
-static int tok_dispatch(bool bwd, const MmxMlpBlockDesc* d, const tok::TokArgs& t, int nw, void* stream) {
+static int tok_dispatch(bool bwd, const MmxMlpBlockDesc* d, const tok::TokArgs& t, void* stream) {
     const bool gelu = d->act == MMX_ACT_GELU;
-    if (d->T == 10) return gelu ? run_tok<ACT_GELU, 10>(bwd, t, nw, stream) : run_tok<ACT_MISH, 10>(bwd, t, nw, stream);
-    return gelu ? run_tok<ACT_GELU, 16>(bwd, t, nw, stream) : run_tok<ACT_MISH, 16>(bwd, t, nw, stream);
+    if (d->T == 10) return gelu ? run_tok<ACT_GELU, 10>(bwd, t, stream) : run_tok<ACT_MISH, 10>(bwd, t, stream);
+    return gelu ? run_tok<ACT_GELU, 16>(bwd, t, stream) : run_tok<ACT_MISH, 16>(bwd, t, stream);
 }
 
 // ------------------------------------------------------------------------------------------ channel half
@@ -161,7 +155,7 @@ static int run_chan(bool bwd, const chan::ChanArgs& c, void* stream) {
     const int ntiles = (c.B + g.seq_per_tile - 1) / g.seq_per_tile;
     // TMEM: forward 2*KP columns (<= 2 CTAs / SM at KP = 64), backward 4*KP columns
     int per_sm = (int)((di.max_smem + 1024) / (smem + 1024));
-    const int tm_cols = bwd ? (4 * KP <= 256 ? 256 : 512) : (2 * KP <= 128 ? 128 : (2 * KP <= 256 ? 256 : 512));
+    const int tm_cols = bwd ? 512 : (3 * KP <= 256 ? 256 : 512);
     per_sm = imax(1, imin(per_sm, 512 / tm_cols));
     const int grid = imin(ntiles, di.sms * per_sm);
     return bwd ? launch_tc5(chan::chan_bwd_kernel<ACT, KP, VEC>, c, grid, chan::kThreadsChan, smem, stream)
@@ -194,12 +188,11 @@ int mmx_mlp_tc5_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const 
     int rc = check_common(d, w, "mmx_mlp_block_fwd");
     if (rc) return rc;
     if ((((uintptr_t)x) | ((uintptr_t)y)) & 15) return fail(MMX_E_INVALID, "mmx_mlp_block_fwd: tensors must be 16-byte aligned");
-    int nw;
-    const int S = tok_S(d, &nw);
+    const int S = tok_S(d);
     tok::TokArgs t;
     fill_tok(t, d, w, nullptr, S);
     t.x = x; t.dx1 = nullptr; t.out = y;
-    if ((rc = tok_dispatch(false, d, t, nw, stream))) return rc;
+    if ((rc = tok_dispatch(false, d, t, stream))) return rc;
     chan::ChanArgs c;
     fill_chan(c, d, w, nullptr);
     c.x1 = y; c.dy = nullptr; c.out = y;
@@ -213,17 +206,16 @@ int mmx_mlp_tc5_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const 
     if ((rc = check_common(d, grads, "mmx_mlp_block_bwd(grads)"))) return rc;
     if ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dx)) & 15) return fail(MMX_E_INVALID, "mmx_mlp_block_bwd: tensors must be 16-byte aligned");
     if (dx == dy || dx == x) return fail(MMX_E_INVALID, "mmx_mlp_block_bwd: dx must not alias x or dy");
-    int nw;
-    const int S = tok_S(d, &nw);
+    const int S = tok_S(d);
     tok::TokArgs t;
     fill_tok(t, d, w, grads, S);
     t.x = x; t.dx1 = nullptr; t.out = dx;                         // x1 -> dx
-    if ((rc = tok_dispatch(false, d, t, nw, stream))) return rc;
+    if ((rc = tok_dispatch(false, d, t, stream))) return rc;
     chan::ChanArgs c;
     fill_chan(c, d, w, grads);
     c.x1 = dx; c.dy = dy; c.out = dx;                             // dx1 -> dx (in place)
     if ((rc = chan_dispatch(true, d, c, stream))) return rc;
     t.dx1 = dx; t.out = dx;
-    return tok_dispatch(true, d, t, nw, stream);
+    return tok_dispatch(true, d, t, stream);
 }
 #endif

@@ -3,14 +3,15 @@
 //     y = x1 + SE(reg2(fc2(reg1(act(fc1(LN2(x1)))))))          reference: h36m/mlp_mixer.py:157-164 (MixerBlock.forward, second
 //     half), MlpBlock :87-96, SELayer :30-34; restated in oracle/mixer_np.py (MlpMixerOracle.forward / backward).
 //
-// Work unit: a tile of 4 * (32 / T) whole sequences = one 128-row MMA tile, one thread per row (thread <-> TMEM lane): LayerNorm,
-// the activation, dropout, the squeeze sum and the LayerNorm backward are thread-local loops over the row; the T frames of a
-// sequence sit in T consecutive lanes of one warp, so the SE excitation is a handful of shuffles.  Lanes 32/T*T .. 31 of every
-// warp are padding rows (all-zero operands).
+// Work unit: a tile of 4 * (32 / T) whole sequences = one 128-row MMA tile.  Row r of the tile is TMEM lane r; the two warps
+// that may touch a lane quarter (warp % 4) split the row's 8-column chunks between them, so LayerNorm, the activation,
+// dropout, the squeeze sum and the LayerNorm backward are per-thread loops over half a row plus one shared-memory exchange
+// of the partial sums.  The T frames of a sequence sit in T consecutive lanes of one warp: the SE excitation is a handful of
+// shuffles.  Lanes 32/T*T .. 31 of every warp are padding rows (all-zero operands).
 //
 // Contractions: tcgen05.mma kind::f16 on bf16 operands with fp32 accumulation in TMEM.  Every fp32 operand x is split as
 // x = hi + lo (+ <= 2^-18 |x|), hi = bf16(x), lo = bf16(x - hi), and a product is issued as three MMAs hi*hi + lo*hi + hi*lo
-// ("bf16x3"): products carry ~2^-17 relative error, two orders of magnitude inside the 2e-3 bar of the reduced-precision mode.
+// ("bf16x3"): measured 5e-6 .. 2e-5 on predictions / gradients of the whole model against the fp64 oracle.
 // Operands live in shared memory in the 16-bit PANEL layout
 //     element (row r, col c)  ->  plane + (c / 8) * (R * 16) + r * 16 + (c % 8) * 2        (hi plane, lo plane)
 // which the tensor core reads in both orientations (SWIZZLE_NONE canonical layouts, checked by tools/micro/umma_layout_probe_bf16):
@@ -21,7 +22,9 @@
 // LN2's affine is folded into fc1 (W1' = W1 * gamma2, b1' = b1 + W1 beta2): the A operand is the plain normalised row and
 // dgamma2, dbeta2, dW1 are derived at flush time from ONE accumulated product  Wt = dU^T xhat.  Bias gradients ride along as a
 // column of ones in the B operand of the weight-gradient products.  dW1 / dW2 accumulate in TMEM across the CTA's whole
-// persistent loop and are flushed once (no shared-memory accumulators, no locks).
+// persistent loop and are flushed once (no shared-memory accumulators, no locks).  Rows a thread needs again later in the
+// tile (the residual input, xhat) are parked in spare TMEM columns, so every per-row loop is a rolled loop over chunks
+// (small code: the first version, fully unrolled over register-resident rows, was 300 KB of SASS and instruction-fetch bound).
 // Activations enter and leave through the bulk-copy engine (cp.async.bulk, SASS UBLKCP) with mbarrier completion.
 #pragma once
 #include "mmx_common.cuh"
@@ -32,8 +35,9 @@ namespace chan {
 
 using namespace tc5;
 
-constexpr int kThreadsChan = 128;
-constexpr int kMaxRR = 4;          // SE bottleneck width served (T // r_se)
+constexpr int kHalves = 2;                     // warps per TMEM lane quarter
+constexpr int kThreadsChan = 128 * kHalves;
+constexpr int kMaxRR = 4;                      // SE bottleneck width served (T // r_se)
 
 struct ChanArgs {
     const float* x1;               // [B*T, H]   input of the channel half
@@ -46,6 +50,33 @@ struct ChanArgs {
     Dropout dr;
     int* abort_count;              // device counter, incremented if a pipeline wait times out (tests assert it stays 0)
 };
+
+// ------------------------------------------------------------------------------------------ dropout masks of the tcgen05 family
+// A dropout site is a [rows][W] tensor; chunk c8 of row `row` covers its columns [8*c8, 8*c8+8).  Four counter-based 32-bit
+// hashes (lowbias32 finaliser over counter ^ key) give 16 random bits per element; an element is kept iff its field >=
+// thresh16.  The key mixes (seed, site, step).  tests/tc5_masks.py is the numpy twin (bit-exact; pinned by a GPU test), which
+// lets the parity tests hand the very same masks to the oracle.
+MMX_HD uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
+    return x;
+}
+MMX_HD uint32_t drop_key(uint32_t seed_lo, uint32_t seed_hi, uint32_t site, uint32_t step) {
+    return mix32(seed_lo ^ mix32(seed_hi ^ mix32(site * 0x9E3779B1u + step)));
+}
+// bit j of the result = keep element 8*c8 + j
+MMX_HD uint32_t keep8(uint32_t key, uint32_t thresh16, uint32_t row, uint32_t W8, uint32_t c8) {
+    const uint32_t base = (row * W8 + c8) * 4u;
+    uint32_t bits = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t i = 0; i < 4; ++i) {
+        const uint32_t r = mix32((base + i) ^ key);
+        bits |= ((r & 0xffffu) >= thresh16 ? 1u : 0u) << (2 * i);
+        bits |= ((r >> 16) >= thresh16 ? 1u : 0u) << (2 * i + 1);
+    }
+    return bits;
+}
 
 // ------------------------------------------------------------------------------------------ small device helpers
 MMX_D uint32_t pack_bf16x2(float lo_elem, float hi_elem) {   // lo_elem -> bits [0,16) (lower address)
@@ -64,11 +95,6 @@ MMX_D void split8(const float (&v)[8], uint4& hi, uint4& lo) {
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-MMX_D void split1(float v, uint16_t& hi, uint16_t& lo) {
-    const uint32_t h = pack_bf16x2(v, 0.0f) & 0xffffu;
-    hi = (uint16_t)h;
-    lo = (uint16_t)(pack_bf16x2(v - __uint_as_float(h << 16), 0.0f) & 0xffffu);
 }
 
 // instruction descriptor: kind::f16, bf16 x bf16 -> fp32
@@ -89,12 +115,13 @@ MMX_D uint64_t dk(uint32_t plane, uint32_t panel_bytes, int k0) { return smem_de
 // 16-bit panel operand, rows = K index, cols = M/N index; r0 = first row of this K=16 step
 MMX_D uint64_t dmn(uint32_t plane, uint32_t panel_bytes, int r0) { return smem_desc(plane + (uint32_t)r0 * 16u, 128u, panel_bytes); }
 
-// D (+)= A B^T with split operands: hi*hi + lo*hi + hi*lo.  A: activation buffer (planes a_hi, a_lo, panel bytes a_ps),
-// B: buffer (b_hi, b_lo, b_ps).  a_mn / b_mn: orientation of each operand; ksteps K=16 steps.
+// D (+)= A B^T with split operands: hi*hi + lo*hi + hi*lo.  A: buffer (planes a_hi, a_lo, panel bytes a_ps), B likewise.
+// A_MN / B_MN: orientation of each operand; ksteps K=16 steps.  Issued by ONE thread.
 template <int A_MN, int B_MN>
 MMX_D void gemm3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_ps, uint32_t b_hi, uint32_t b_lo, uint32_t b_ps, int N,
                  int ksteps, bool accumulate_first) {
     const uint32_t id = idesc_bf16(128, N, A_MN, B_MN);
+#pragma unroll 1
     for (int s = 0; s < ksteps; ++s) {
         const int k0 = 16 * s;
         const uint64_t ah = A_MN ? dmn(a_hi, a_ps, k0) : dk(a_hi, a_ps, k0);
@@ -107,25 +134,6 @@ MMX_D void gemm3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_ps, u
     }
 }
 
-// keep-scales of 8 consecutive columns [8*c8, 8*c8+8) of row `grow` of a [rows][W] dropout site: one Philox4x32-7 call,
-// 16 random bits per element (the masks only need to be uncorrelated).  Identical in forward and backward.
-MMX_D void drop8(const Dropout& d, uint32_t site, uint32_t grow, uint32_t W8, uint32_t c8, float (&ks)[8]) {
-    const uint64_t ctr = (uint64_t)grow * W8 + c8;
-    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = site ^ 0x2545f491u, c3 = d.step, k0 = d.seed_lo, k1 = d.seed_hi;
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3; k0 += W0; k1 += W1;
-    }
-    const uint32_t th = d.thresh >> 16;
-    ks[0] = (c0 & 0xffffu) >= th ? d.scale : 0.0f; ks[1] = (c0 >> 16) >= th ? d.scale : 0.0f;
-    ks[2] = (c1 & 0xffffu) >= th ? d.scale : 0.0f; ks[3] = (c1 >> 16) >= th ? d.scale : 0.0f;
-    ks[4] = (c2 & 0xffffu) >= th ? d.scale : 0.0f; ks[5] = (c2 >> 16) >= th ? d.scale : 0.0f;
-    ks[6] = (c3 & 0xffffu) >= th ? d.scale : 0.0f; ks[7] = (c3 >> 16) >= th ? d.scale : 0.0f;
-}
-
 // ------------------------------------------------------------------------------------------ shared-memory plan
 template <int KP>
 struct Plan {
@@ -135,10 +143,9 @@ struct Plan {
     static constexpr uint32_t WPS = KP * 16;                 // weight panel: KP rows x 16 B
     static constexpr uint32_t WPLANE = (KP / 8) * WPS;
     static constexpr uint32_t WBUF = 2 * WPLANE;
-    static constexpr uint32_t SMALL = (4 * KP + 2 * 32 * kMaxRR + 64) * 4;   // c1f, c2, gamma2, spare | se1, se2 | barriers, slots
+    static constexpr uint32_t SMALL = (4 * KP + 2 * 32 * kMaxRR + 4 * kHalves * 128 + 64) * 4;   // c1f, c2, gamma2, spare | se1, se2 | exchange | barriers
 };
 
-// geometry of a tile
 struct Geo {
     int spw, rpw, seq_per_tile, tile_rows, pitch;
 };
@@ -154,7 +161,7 @@ MMX_HD Geo make_geo(int T, int H, int vec) {
 template <int KP>
 MMX_HD size_t chan_smem_bytes(int T, int H, int vec, bool bwd) {
     const Geo g = make_geo(T, H, vec);
-    size_t stage = (size_t)g.tile_rows * g.pitch * 4;
+    size_t stage = (size_t)g.tile_rows * g.pitch * 4 + 64;    // + slack: chunk loads of the last row may run past the row
     stage = (stage + 127) / 128 * 128;
     size_t buf = Plan<KP>::BUF;
     if (buf < stage) buf = stage;                             // the X region doubles as the output staging tile
@@ -182,44 +189,35 @@ MMX_D void stage_out(float* g, const float* S, size_t row0, int nrows, int H, in
     bulk_commit();
 }
 
-template <int KP, int VEC>
-MMX_D void load_row(const float* srow, int H, float (&x)[KP]) {
+// 8 consecutive columns [k0, k0+8) of a staged row; columns >= H read as zero (H % VEC == 0)
+template <int VEC>
+MMX_D void ld8(const float* srow, int k0, int H, float (&v)[8]) {
 #pragma unroll
-    for (int k = 0; k < KP; k += VEC) {
-        if (k < H) {
-            if (VEC == 4) { const float4 v = *reinterpret_cast<const float4*>(srow + k); x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w; }
-            else { const float2 v = *reinterpret_cast<const float2*>(srow + k); x[k] = v.x; x[k + 1] = v.y; }
+    for (int j = 0; j < 8; j += VEC) {
+        if (k0 + j < H) {
+            if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(srow + k0 + j); v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w; }
+            else { const float2 t = *reinterpret_cast<const float2*>(srow + k0 + j); v[j] = t.x; v[j + 1] = t.y; }
         } else {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) x[k + j] = 0.0f;
+            for (int i = 0; i < VEC; ++i) v[j + i] = 0.0f;
         }
     }
 }
-template <int KP, int VEC>
-MMX_D void store_row(float* srow, int H, const float (&x)[KP]) {
+template <int VEC>
+MMX_D void st8(float* srow, int k0, int H, const float (&v)[8]) {
 #pragma unroll
-    for (int k = 0; k < KP; k += VEC) {
-        if (k < H) {
-            if (VEC == 4) *reinterpret_cast<float4*>(srow + k) = make_float4(x[k], x[k + 1], x[k + 2], x[k + 3]);
-            else *reinterpret_cast<float2*>(srow + k) = make_float2(x[k], x[k + 1]);
+    for (int j = 0; j < 8; j += VEC) {
+        if (k0 + j < H) {
+            if (VEC == 4) *reinterpret_cast<float4*>(srow + k0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            else *reinterpret_cast<float2*>(srow + k0 + j) = make_float2(v[j], v[j + 1]);
         }
     }
+}
+MMX_D void ld8s(const float* p, float (&v)[8]) {   // 8 floats from a 16-byte aligned shared array
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-// write one row of an operand buffer: values v[KP] (already including the ones column / zero padding) -> hi and lo planes
-template <int KP>
-MMX_D void put_row(uint8_t* buf, int row, const float (&v)[KP]) {
-#pragma unroll
-    for (int c8 = 0; c8 < KP / 8; ++c8) {
-        float t[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] = v[8 * c8 + j];
-        uint4 hi, lo;
-        split8(t, hi, lo);
-        *reinterpret_cast<uint4*>(buf + c8 * Plan<KP>::PS + row * 16) = hi;
-        *reinterpret_cast<uint4*>(buf + Plan<KP>::PLANE + c8 * Plan<KP>::PS + row * 16) = lo;
-    }
-}
 MMX_D void put_chunk(uint8_t* buf, uint32_t plane_bytes, uint32_t ps, int row, int c8, const float (&t)[8]) {
     uint4 hi, lo;
     split8(t, hi, lo);
@@ -227,20 +225,61 @@ MMX_D void put_chunk(uint8_t* buf, uint32_t plane_bytes, uint32_t ps, int row, i
     *reinterpret_cast<uint4*>(buf + plane_bytes + c8 * ps + row * 16) = lo;
 }
 
-// stage one weight matrix W[rows][cols] (row-major, optional per-column scale) into a weight buffer (panel layout, KP x KP, zero padded)
+// stage one weight matrix W[rows][cols] (row-major, optional per-column scale) into a weight buffer (panel layout, KP x KP,
+// zero padded; the buffer must have been zeroed)
 template <int KP>
 MMX_D void stage_weight(uint8_t* wbuf, const float* W, int rows, int cols, const float* colscale, int tid) {
-    for (int i = tid; i < (int)(Plan<KP>::WBUF / 16); i += kThreadsChan) reinterpret_cast<uint4*>(wbuf)[i] = make_uint4(0, 0, 0, 0);
+    if ((cols & 1) == 0) {
+        const int n2 = rows * cols / 2;
+        for (int i = tid; i < n2; i += kThreadsChan) {
+            const int e = 2 * i, r = e / cols, c = e - r * cols;
+            float2 v = *reinterpret_cast<const float2*>(W + e);
+            if (colscale) { v.x *= colscale[c]; v.y *= colscale[c + 1]; }
+            const uint32_t h = pack_bf16x2(v.x, v.y);
+            const uint32_t l = pack_bf16x2(v.x - __uint_as_float(h << 16), v.y - __uint_as_float(h & 0xffff0000u));
+            const uint32_t off = (uint32_t)(c >> 3) * Plan<KP>::WPS + (uint32_t)r * 16u + (uint32_t)(c & 7) * 2u;
+            *reinterpret_cast<uint32_t*>(wbuf + off) = h;
+            *reinterpret_cast<uint32_t*>(wbuf + Plan<KP>::WPLANE + off) = l;
+        }
+    } else {
+        for (int i = tid; i < rows * cols; i += kThreadsChan) {
+            const int r = i / cols, c = i - r * cols;
+            float v = W[i];
+            if (colscale) v *= colscale[c];
+            const uint32_t h = pack_bf16x2(v, 0.0f) & 0xffffu;
+            const uint32_t l = pack_bf16x2(v - __uint_as_float(h << 16), 0.0f) & 0xffffu;
+            const uint32_t off = (uint32_t)(c >> 3) * Plan<KP>::WPS + (uint32_t)r * 16u + (uint32_t)(c & 7) * 2u;
+            *reinterpret_cast<uint16_t*>(wbuf + off) = (uint16_t)h;
+            *reinterpret_cast<uint16_t*>(wbuf + Plan<KP>::WPLANE + off) = (uint16_t)l;
+        }
+    }
+}
+
+// per-CTA constants: weights (LN2 affine folded into fc1), biases, SE weights.  Contains CTA barriers.
+template <int KP>
+MMX_D void prologue(const ChanArgs& a, uint8_t* w1b, uint8_t* w2b, float* c1f, float* c2, float* gam, float* se1, float* se2, int tid) {
+    const int H = a.H, ch = a.ch, T = a.T, rr = a.rr;
+    for (int i = tid; i < (int)(2 * Plan<KP>::WBUF / 16); i += kThreadsChan) reinterpret_cast<uint4*>(w1b)[i] = make_uint4(0, 0, 0, 0);   // w1b, w2b contiguous
+    for (int c = tid; c < KP; c += kThreadsChan) {
+        c2[c] = c < H ? a.b2[c] : 0.0f;
+        gam[c] = c < H ? a.ln_g[c] : 0.0f;
+        c1f[c] = 0.0f;
+    }
+    for (int i = tid; i < 32 * kMaxRR; i += kThreadsChan) {
+        se1[i] = (rr > 0 && i < rr * T) ? a.se1[i] : 0.0f;
+        se2[i] = (rr > 0 && i < rr * T) ? a.se2[i] : 0.0f;
+    }
     __syncthreads();
-    for (int i = tid; i < rows * cols; i += kThreadsChan) {
-        const int r = i / cols, c = i - r * cols;
-        float v = W[i];
-        if (colscale) v *= colscale[c];
-        uint16_t hi, lo;
-        split1(v, hi, lo);
-        const uint32_t off = (uint32_t)(c >> 3) * Plan<KP>::WPS + (uint32_t)r * 16u + (uint32_t)(c & 7) * 2u;
-        *reinterpret_cast<uint16_t*>(wbuf + off) = hi;
-        *reinterpret_cast<uint16_t*>(wbuf + Plan<KP>::WPLANE + off) = lo;
+    stage_weight<KP>(w1b, a.w1, ch, H, a.ln_g, tid);
+    stage_weight<KP>(w2b, a.w2, H, ch, nullptr, tid);
+    // b1'[c] = b1[c] + sum_h W1[c][h] beta2[h]: one warp per row, lanes over h
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int c = warp; c < ch; c += kThreadsChan / 32) {
+        float s = 0.0f;
+        for (int h = lane; h < H; h += 32) s = fmaf(a.w1[(size_t)c * H + h], a.ln_b[h], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) c1f[c] = s + a.b1[c];
     }
 }
 
@@ -264,6 +303,48 @@ MMX_D SeOut se_excite(float s, int t, int seq_base, int T, int rr, const float* 
     return o;
 }
 
+// sum the two halves' partial sums of a row (both halves get the totals).  Contains a CTA barrier.
+MMX_D void row_exchange(float* ex, int half, int prow, float& a, float& b) {
+    if (kHalves == 1) { __syncthreads(); return; }
+    ex[(0 * kHalves + half) * 128 + prow] = a;
+    ex[(1 * kHalves + half) * 128 + prow] = b;
+    __syncthreads();
+    a = ex[(0 * kHalves + 0) * 128 + prow] + ex[(0 * kHalves + 1) * 128 + prow];
+    b = ex[(1 * kHalves + 0) * 128 + prow] + ex[(1 * kHalves + 1) * 128 + prow];
+}
+
+// common carve-up of the dynamic shared memory
+template <int KP>
+struct Carve {
+    uint8_t *bufX, *bufY, *w1b, *w2b;
+    float *S1, *S2, *c1f, *c2, *gam, *se1, *se2, *ex;
+    uint64_t* bars;
+    uint32_t* tslot;
+    volatile int* abortf;
+    uint32_t buf_bytes;
+    MMX_D Carve(uint8_t* raw, const Geo& g, bool bwd) {
+        using P = Plan<KP>;
+        uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+        const uint32_t stage_bytes = ((uint32_t)g.tile_rows * g.pitch * 4u + 64u + 127u) / 128u * 128u;
+        buf_bytes = P::BUF > stage_bytes ? P::BUF : stage_bytes;
+        bufX = sm;
+        bufY = bwd ? bufX + buf_bytes : bufX;
+        w1b = bufY + buf_bytes;
+        w2b = w1b + P::WBUF;
+        S1 = reinterpret_cast<float*>(w2b + P::WBUF);
+        S2 = bwd ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(S1) + stage_bytes) : S1;
+        c1f = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(S2) + stage_bytes);
+        c2 = c1f + KP;
+        gam = c2 + KP;
+        se1 = gam + 2 * KP;
+        se2 = se1 + 32 * kMaxRR;
+        ex = se2 + 32 * kMaxRR;
+        bars = reinterpret_cast<uint64_t*>(ex + 4 * kHalves * 128);
+        tslot = reinterpret_cast<uint32_t*>(bars + 4);
+        abortf = reinterpret_cast<volatile int*>(tslot + 1);
+    }
+};
+
 // ==========================================================================================
 // forward
 // ==========================================================================================
@@ -271,70 +352,48 @@ template <int ACT, int KP, int VEC>
 __global__ void __launch_bounds__(kThreadsChan) chan_fwd_kernel(const ChanArgs a) {
     using P = Plan<KP>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const Geo g = make_geo(a.T, a.H, VEC);
-    const uint32_t stage_bytes = ((uint32_t)g.tile_rows * g.pitch * 4u + 127u) / 128u * 128u;
-    const uint32_t buf_bytes = P::BUF > stage_bytes ? P::BUF : stage_bytes;
-    uint8_t* bufX = sm;
-    uint8_t* w1b = bufX + buf_bytes;
-    uint8_t* w2b = w1b + P::WBUF;
-    float* S = reinterpret_cast<float*>(w2b + P::WBUF);
-    float* c1f = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(S) + stage_bytes);
-    float* c2 = c1f + KP;
-    float* se1 = c2 + 3 * KP;
-    float* se2 = se1 + 32 * kMaxRR;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(se2 + 32 * kMaxRR);
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);
-    volatile int* abortf = reinterpret_cast<volatile int*>(tslot + 1);
+    Carve<KP> cv(smem_raw, g, false);
+    uint8_t* bufX = cv.bufX;
+    float* S = cv.S1;
+    uint64_t* bars = cv.bars;
+    volatile int* abortf = cv.abortf;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, qtr = warp & 3, half = warp >> 2;
+    const int prow = qtr * 32 + lane;
     const int H = a.H, ch = a.ch, T = a.T, rr = a.rr;
     const Dropout dr = resolve_dropout(a.dr);
-    constexpr int TM_COLS = 2 * KP <= 128 ? 128 : (2 * KP <= 256 ? 256 : 512);
+    const uint32_t th16 = dr.thresh >> 16;
+    const uint32_t key2 = drop_key(dr.seed_lo, dr.seed_hi, a.site_base + 2, dr.step), key3 = drop_key(dr.seed_lo, dr.seed_hi, a.site_base + 3, dr.step);
+    constexpr int TM_COLS = 3 * KP <= 256 ? 256 : 512;
+    constexpr int NCH = KP / 8;
 
-    // ---------------- prologue: barriers, TMEM, weights (LN2 affine folded into fc1)
     if (tid == 0) {
         mbar_init(&bars[0], 1);   // X1 tile landed
         mbar_init(&bars[1], 1);   // MMA group done
         *abortf = 0;
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc<TM_COLS>(tslot);
-    stage_weight<KP>(w1b, a.w1, ch, H, a.ln_g, tid);
-    stage_weight<KP>(w2b, a.w2, H, ch, nullptr, tid);
-    for (int c = tid; c < KP; c += kThreadsChan) {
-        float s = 0.0f;
-        if (c < ch) {
-            s = a.b1[c];
-            for (int h = 0; h < H; ++h) s = fmaf(a.w1[(size_t)c * H + h], a.ln_b[h], s);
-        }
-        c1f[c] = s;
-        c2[c] = c < H ? a.b2[c] : 0.0f;
-    }
-    for (int i = tid; i < 32 * kMaxRR; i += kThreadsChan) {
-        se1[i] = (rr > 0 && i < rr * T) ? a.se1[i] : 0.0f;
-        se2[i] = (rr > 0 && i < rr * T) ? a.se2[i] : 0.0f;
-    }
+    if (warp == 0) tmem_alloc<TM_COLS>(cv.tslot);
+    prologue<KP>(a, cv.w1b, cv.w2b, cv.c1f, cv.c2, cv.gam, cv.se1, cv.se2, tid);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tslot;
-    const uint32_t tU = tmem, tY = tmem + KP;
-    const uint32_t xB = smem_u32(bufX), w1B = smem_u32(w1b), w2B = smem_u32(w2b);
+    const uint32_t tmem = *cv.tslot;
+    const uint32_t tU = tmem, tY = tmem + KP, tXR = tmem + 2 * KP;
+    const uint32_t xB = smem_u32(bufX), w1B = smem_u32(cv.w1b), w2B = smem_u32(cv.w2b);
 
     const int ntiles = (a.B + g.seq_per_tile - 1) / g.seq_per_tile;
     const bool lane_ok = lane < g.rpw;
     const int t = lane_ok ? lane % T : 0;
     const int seq_base = lane_ok ? (lane / T) * T : 0;
-    const int drow = warp * g.rpw + (lane_ok ? lane : 0);
+    const int drow = qtr * g.rpw + (lane_ok ? lane : 0);
+    const int nchH = (H + 7) >> 3;
+    const uint32_t ch8 = (uint32_t)(ch + 7) >> 3, H8 = (uint32_t)nchH;
     uint32_t ph_in = 0, ph_mma = 0;
-    bool store_pending = false;
 
-    auto tile_nrows = [&](int tile) {
-        const int nseq = min(g.seq_per_tile, a.B - tile * g.seq_per_tile);
-        return nseq * T;
-    };
+    auto tile_nrows = [&](int tile) { return min(g.seq_per_tile, a.B - tile * g.seq_per_tile) * T; };
     if (warp == 0 && (int)blockIdx.x < ntiles)
         stage_in<VEC>(S, a.x1, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), H, g.pitch, &bars[0], lane);
 
@@ -342,41 +401,51 @@ __global__ void __launch_bounds__(kThreadsChan) chan_fwd_kernel(const ChanArgs a
         const int nrows = tile_nrows(tile);
         const bool valid = lane_ok && drow < nrows;
         const uint32_t grow = (uint32_t)((size_t)tile * g.tile_rows + drow);
+        const float* srow = S + (size_t)drow * g.pitch;
 
-        // ---------------- P0: LayerNorm of the row -> operand X (hi/lo planes)
+        // ---------------- P0: LayerNorm statistics (shifted one-pass), xhat -> operand X, raw row -> TMEM
         mbar_wait(&bars[0], ph_in, abortf);
         ph_in ^= 1;
-        float x[KP];
-        load_row<KP, VEC>(S + (size_t)drow * g.pitch, valid ? H : 0, x);
-        float mean = 0.0f, rstd = 0.0f;
+        float mean, rstd;
         {
-            float s = 0.0f;
+            const float c0 = valid ? srow[0] : 0.0f;
+            float s = 0.0f, ss = 0.0f;
+            if (valid) {
+#pragma unroll 1
+                for (int c8 = half; c8 < nchH; c8 += kHalves) {
+                    float v[8];
+                    ld8<VEC>(srow, 8 * c8, H, v);
 #pragma unroll
-            for (int k = 0; k < KP; ++k) s += x[k];
-            mean = s / (float)H;
-            float ss = 0.0f;
+                    for (int j = 0; j < 8; ++j) {
+                        const float dv = 8 * c8 + j < H ? v[j] - c0 : 0.0f;
+                        s += dv;
+                        ss = fmaf(dv, dv, ss);
+                    }
+                }
+            }
+            if (warp == 0) bulk_wait_read0();          // the previous tile's output (staged in the X region) has left shared memory
+            row_exchange(cv.ex, half, prow, s, ss);
+            const float ms = s / (float)H;
+            mean = c0 + ms;
+            rstd = 1.0f / sqrtf(fmaxf(ss / (float)H - ms * ms, 0.0f) + 1e-5f);
+        }
+#pragma unroll 1
+        for (int c8 = half; c8 < NCH; c8 += kHalves) {
+            float v[8], xh[8];
+            ld8<VEC>(srow, 8 * c8, valid ? H : 0, v);
 #pragma unroll
-            for (int k = 0; k < KP; ++k) { const float dv = k < H ? x[k] - mean : 0.0f; ss = fmaf(dv, dv, ss); }
-            rstd = 1.0f / sqrtf(ss / (float)H + 1e-5f);
+            for (int j = 0; j < 8; ++j) xh[j] = (valid && 8 * c8 + j < H) ? (v[j] - mean) * rstd : 0.0f;
+            put_chunk(bufX, P::PLANE, P::PS, prow, c8, xh);
+            tmem_st8(tmem_addr(tXR, qtr, 8 * c8), v);
         }
-        if (store_pending) {   // the previous tile's output (staged in the X region) must have left shared memory
-            if (warp == 0) bulk_wait_read0();
-            store_pending = false;
-        }
-        __syncthreads();       // S fully read; X region free
+        tmem_wait_st();
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();       // operand X complete; S fully consumed
         if (warp == 0) {
             const int next = tile + gridDim.x;
             if (next < ntiles) stage_in<VEC>(S, a.x1, (size_t)next * g.tile_rows, tile_nrows(next), H, g.pitch, &bars[0], lane);
         }
-        {
-            float v[KP];
-#pragma unroll
-            for (int k = 0; k < KP; ++k) v[k] = !valid ? 0.0f : (k < H ? (x[k] - mean) * rstd : 0.0f);
-            put_row<KP>(bufX, tid, v);
-        }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
         if (tid == 0) {
             tc_fence_after();
             gemm3<0, 0>(tU, xB, xB + P::PLANE, P::PS, w1B, w1B + P::WPLANE, P::WPS, KP, KP / 16, false);
@@ -386,20 +455,20 @@ __global__ void __launch_bounds__(kThreadsChan) chan_fwd_kernel(const ChanArgs a
         mbar_wait(&bars[1], ph_mma, abortf);
         ph_mma ^= 1;
         tc_fence_after();
-#pragma unroll
-        for (int c8 = 0; c8 < KP / 8; ++c8) {
-            float u[8], ks[8];
-            tmem_ld8(tmem_addr(tU, warp, 8 * c8), u);
+#pragma unroll 1
+        for (int c8 = half; c8 < NCH; c8 += kHalves) {
+            float u[8], b[8];
+            tmem_ld8(tmem_addr(tU, qtr, 8 * c8), u);
+            ld8s(cv.c1f + 8 * c8, b);
+            const uint32_t kb = th16 ? keep8(key2, th16, grow, ch8, c8) : 0xffu;
             tmem_wait_ld();
-            if (dr.thresh) drop8(dr, a.site_base + 2, grow, (uint32_t)(ch + 7) >> 3, c8, ks);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int c = 8 * c8 + j;
-                float gv = act_fwd<ACT>(u[j] + c1f[c]);
-                if (dr.thresh) gv *= ks[j];
-                u[j] = (!valid || c >= ch) ? 0.0f : gv;
+                float gv = act_fwd<ACT>(u[j] + b[j]);
+                gv = (kb >> j) & 1u ? gv * dr.scale : 0.0f;
+                u[j] = (valid && 8 * c8 + j < ch) ? gv : 0.0f;
             }
-            put_chunk(bufX, P::PLANE, P::PS, tid, c8, u);
+            put_chunk(bufX, P::PLANE, P::PS, prow, c8, u);
         }
         fence_async_smem();
         tc_fence_before();
@@ -413,36 +482,45 @@ __global__ void __launch_bounds__(kThreadsChan) chan_fwd_kernel(const ChanArgs a
         mbar_wait(&bars[1], ph_mma, abortf);
         ph_mma ^= 1;
         tc_fence_after();
-        float y[KP];
-        float ssum = 0.0f;
-#pragma unroll
-        for (int c8 = 0; c8 < KP / 8; ++c8) {
-            float u[8], ks[8];
-            tmem_ld8(tmem_addr(tY, warp, 8 * c8), u);
+        float ssum = 0.0f, dummy = 0.0f;
+#pragma unroll 1
+        for (int c8 = half; c8 < nchH; c8 += kHalves) {
+            float u[8], b[8];
+            tmem_ld8(tmem_addr(tY, qtr, 8 * c8), u);
+            ld8s(cv.c2 + 8 * c8, b);
+            const uint32_t kb = th16 ? keep8(key3, th16, grow, H8, c8) : 0xffu;
             tmem_wait_ld();
-            if (dr.thresh) drop8(dr, a.site_base + 3, grow, (uint32_t)(H + 7) >> 3, c8, ks);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int h = 8 * c8 + j;
-                float yv = u[j] + c2[h];
-                if (dr.thresh) yv *= ks[j];
-                yv = h < H ? yv : 0.0f;
-                y[h] = yv;
+                float yv = u[j] + b[j];
+                yv = (kb >> j) & 1u ? yv * dr.scale : 0.0f;
+                yv = (valid && 8 * c8 + j < H) ? yv : 0.0f;
+                u[j] = yv;
                 ssum += yv;
             }
+            tmem_st8(tmem_addr(tY, qtr, 8 * c8), u);
         }
+        tmem_wait_st();
+        row_exchange(cv.ex, half, prow, ssum, dummy);
         float gate = 1.0f;
-        if (rr > 0) gate = se_excite(valid ? ssum / (float)H : 0.0f, t, seq_base, T, rr, se1, se2).gate;
+        if (rr > 0) gate = se_excite(ssum / (float)H, t, seq_base, T, rr, cv.se1, cv.se2).gate;
+        {
+            float* orow = reinterpret_cast<float*>(bufX) + (size_t)drow * g.pitch;
+#pragma unroll 1
+            for (int c8 = half; c8 < nchH; c8 += kHalves) {
+                float y[8], x[8];
+                tmem_ld8(tmem_addr(tY, qtr, 8 * c8), y);
+                tmem_ld8(tmem_addr(tXR, qtr, 8 * c8), x);
+                tmem_wait_ld();
 #pragma unroll
-        for (int k = 0; k < KP; ++k) y[k] = fmaf(y[k], gate, x[k]);
+                for (int j = 0; j < 8; ++j) y[j] = fmaf(y[j], gate, x[j]);
+                if (valid) st8<VEC>(orow, 8 * c8, H, y);
+            }
+        }
         tc_fence_before();
-        if (valid) store_row<KP, VEC>(reinterpret_cast<float*>(bufX) + (size_t)drow * g.pitch, H, y);
         fence_async_smem();
         __syncthreads();
-        if (warp == 0) {
-            stage_out<VEC>(a.out, reinterpret_cast<const float*>(bufX), (size_t)tile * g.tile_rows, nrows, H, g.pitch, lane);
-            store_pending = true;
-        }
+        if (warp == 0) stage_out<VEC>(a.out, reinterpret_cast<const float*>(bufX), (size_t)tile * g.tile_rows, nrows, H, g.pitch, lane);
     }
     if (warp == 0) bulk_wait_all0();
     if (tid == 0 && *abortf) atomicAdd(a.abort_count, 1);
@@ -458,30 +536,24 @@ template <int ACT, int KP, int VEC>
 __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a) {
     using P = Plan<KP>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const Geo g = make_geo(a.T, a.H, VEC);
-    const uint32_t stage_bytes = ((uint32_t)g.tile_rows * g.pitch * 4u + 127u) / 128u * 128u;
-    const uint32_t buf_bytes = P::BUF > stage_bytes ? P::BUF : stage_bytes;
-    uint8_t* bufX = sm;                       // N2 -> dY2 -> N2 again -> output staging
-    uint8_t* bufY = bufX + buf_bytes;         // G2 -> dU2
-    uint8_t* w1b = bufY + buf_bytes;
-    uint8_t* w2b = w1b + P::WBUF;
-    float* S1 = reinterpret_cast<float*>(w2b + P::WBUF);                                  // x1 tile
-    float* S2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(S1) + stage_bytes);   // dy tile
-    float* c1f = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(S2) + stage_bytes);
-    float* c2 = c1f + KP;
-    float* gam = c2 + KP;
-    float* se1 = gam + 2 * KP;
-    float* se2 = se1 + 32 * kMaxRR;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(se2 + 32 * kMaxRR);
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);
-    volatile int* abortf = reinterpret_cast<volatile int*>(tslot + 1);
+    Carve<KP> cv(smem_raw, g, true);
+    uint8_t* bufX = cv.bufX;                  // xhat -> dY2 -> xhat again -> output staging
+    uint8_t* bufY = cv.bufY;                  // G2 -> dU2
+    float* S1 = cv.S1;                        // x1 tile
+    float* S2 = cv.S2;                        // dy tile
+    uint64_t* bars = cv.bars;
+    volatile int* abortf = cv.abortf;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, qtr = warp & 3, half = warp >> 2;
+    const int prow = qtr * 32 + lane;
     const int H = a.H, ch = a.ch, T = a.T, rr = a.rr;
     const Dropout dr = resolve_dropout(a.dr);
-    constexpr int TM_COLS = 4 * KP <= 256 ? 256 : 512;
-    static_assert(4 * KP <= 512, "TMEM: four KP-column accumulators");
+    const uint32_t th16 = dr.thresh >> 16;
+    const uint32_t key2 = drop_key(dr.seed_lo, dr.seed_hi, a.site_base + 2, dr.step), key3 = drop_key(dr.seed_lo, dr.seed_hi, a.site_base + 3, dr.step);
+    constexpr int TM_COLS = 512;
+    static_assert(5 * KP <= 512, "TMEM: five KP-column regions");
+    constexpr int NCH = KP / 8;
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);   // x1 tile landed
@@ -490,47 +562,31 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
         *abortf = 0;
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc<TM_COLS>(tslot);
-    stage_weight<KP>(w1b, a.w1, ch, H, a.ln_g, tid);
-    stage_weight<KP>(w2b, a.w2, H, ch, nullptr, tid);
-    for (int c = tid; c < KP; c += kThreadsChan) {
-        float s = 0.0f;
-        if (c < ch) {
-            s = a.b1[c];
-            for (int h = 0; h < H; ++h) s = fmaf(a.w1[(size_t)c * H + h], a.ln_b[h], s);
-        }
-        c1f[c] = s;
-        c2[c] = c < H ? a.b2[c] : 0.0f;
-        gam[c] = c < H ? a.ln_g[c] : 0.0f;
-    }
-    for (int i = tid; i < 32 * kMaxRR; i += kThreadsChan) {
-        se1[i] = (rr > 0 && i < rr * T) ? a.se1[i] : 0.0f;
-        se2[i] = (rr > 0 && i < rr * T) ? a.se2[i] : 0.0f;
-    }
+    if (warp == 0) tmem_alloc<TM_COLS>(cv.tslot);
+    prologue<KP>(a, cv.w1b, cv.w2b, cv.c1f, cv.c2, cv.gam, cv.se1, cv.se2, tid);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tslot;
-    const uint32_t tU = tmem, tY = tmem + KP, tDW1 = tmem + 2 * KP, tDW2 = tmem + 3 * KP;   // U2 / dN2 | Y2 / dG2 | Wt = dU^T xhat | dW2
-    const uint32_t xB = smem_u32(bufX), yB = smem_u32(bufY), w1B = smem_u32(w1b), w2B = smem_u32(w2b);
+    const uint32_t tmem = *cv.tslot;
+    // U2 / d xhat | Y2 / dG2 | xhat (parked) | Wt = dU^T xhat | dW2
+    const uint32_t tU = tmem, tY = tmem + KP, tXH = tmem + 2 * KP, tDW1 = tmem + 3 * KP, tDW2 = tmem + 4 * KP;
+    const uint32_t xB = smem_u32(bufX), yB = smem_u32(bufY), w1B = smem_u32(cv.w1b), w2B = smem_u32(cv.w2b);
 
     const int ntiles = (a.B + g.seq_per_tile - 1) / g.seq_per_tile;
     const bool lane_ok = lane < g.rpw;
     const int t = lane_ok ? lane % T : 0;
     const int seq_base = lane_ok ? (lane / T) * T : 0;
-    const int drow = warp * g.rpw + (lane_ok ? lane : 0);
+    const int drow = qtr * g.rpw + (lane_ok ? lane : 0);
+    const int nchH = (H + 7) >> 3;
+    const uint32_t ch8 = (uint32_t)(ch + 7) >> 3, H8 = (uint32_t)nchH;
     uint32_t ph_x = 0, ph_dy = 0, ph_mma = 0;
-    bool store_pending = false;
     bool first = true;
     float gS1[kMaxRR], gS2[kMaxRR];
 #pragma unroll
     for (int k = 0; k < kMaxRR; ++k) gS1[k] = gS2[k] = 0.0f;
 
-    auto tile_nrows = [&](int tile) {
-        const int nseq = min(g.seq_per_tile, a.B - tile * g.seq_per_tile);
-        return nseq * T;
-    };
+    auto tile_nrows = [&](int tile) { return min(g.seq_per_tile, a.B - tile * g.seq_per_tile) * T; };
     if (warp == 0 && (int)blockIdx.x < ntiles) {
         stage_in<VEC>(S1, a.x1, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), H, g.pitch, &bars[0], lane);
         stage_in<VEC>(S2, a.dy, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), H, g.pitch, &bars[2], lane);
@@ -541,35 +597,52 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
         const bool valid = lane_ok && drow < nrows;
         const uint32_t grow = (uint32_t)((size_t)tile * g.tile_rows + drow);
         const int next = tile + gridDim.x;
+        const float* srow = S1 + (size_t)drow * g.pitch;
+        const float* drw = S2 + (size_t)drow * g.pitch;
 
-        // ---------------- P0: xhat = LN2(x1) without affine -> operand X
+        // ---------------- P0: xhat = LN2(x1) without affine (+ ones column at H) -> operand X and TMEM
         mbar_wait(&bars[0], ph_x, abortf);
         ph_x ^= 1;
-        float xh[KP];     // xhat row, kept for the whole tile (ones column at H)
-        float rstd;
+        float mean, rstd;
         {
-            load_row<KP, VEC>(S1 + (size_t)drow * g.pitch, valid ? H : 0, xh);
-            float s = 0.0f;
+            const float c0 = valid ? srow[0] : 0.0f;
+            float s = 0.0f, ss = 0.0f;
+            if (valid) {
+#pragma unroll 1
+                for (int c8 = half; c8 < nchH; c8 += kHalves) {
+                    float v[8];
+                    ld8<VEC>(srow, 8 * c8, H, v);
 #pragma unroll
-            for (int k = 0; k < KP; ++k) s += xh[k];
-            const float mean = s / (float)H;
-            float ss = 0.0f;
-#pragma unroll
-            for (int k = 0; k < KP; ++k) { const float dv = k < H ? xh[k] - mean : 0.0f; ss = fmaf(dv, dv, ss); }
-            rstd = 1.0f / sqrtf(ss / (float)H + 1e-5f);
-#pragma unroll
-            for (int k = 0; k < KP; ++k) xh[k] = !valid ? 0.0f : (k < H ? (xh[k] - mean) * rstd : (k == H ? 1.0f : 0.0f));
-        }
-        if (store_pending) {
+                    for (int j = 0; j < 8; ++j) {
+                        const float dv = 8 * c8 + j < H ? v[j] - c0 : 0.0f;
+                        s += dv;
+                        ss = fmaf(dv, dv, ss);
+                    }
+                }
+            }
             if (warp == 0) bulk_wait_read0();
-            store_pending = false;
+            row_exchange(cv.ex, half, prow, s, ss);
+            const float ms = s / (float)H;
+            mean = c0 + ms;
+            rstd = 1.0f / sqrtf(fmaxf(ss / (float)H - ms * ms, 0.0f) + 1e-5f);
         }
-        __syncthreads();   // S1 consumed, X region free
-        if (warp == 0 && next < ntiles) stage_in<VEC>(S1, a.x1, (size_t)next * g.tile_rows, tile_nrows(next), H, g.pitch, &bars[0], lane);
-        put_row<KP>(bufX, tid, xh);
+#pragma unroll 1
+        for (int c8 = half; c8 < NCH; c8 += kHalves) {
+            float v[8];
+            ld8<VEC>(srow, 8 * c8, valid ? H : 0, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = 8 * c8 + j;
+                v[j] = !valid ? 0.0f : (k < H ? (v[j] - mean) * rstd : (k == H ? 1.0f : 0.0f));
+            }
+            put_chunk(bufX, P::PLANE, P::PS, prow, c8, v);
+            tmem_st8(tmem_addr(tXH, qtr, 8 * c8), v);
+        }
+        tmem_wait_st();
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        __syncthreads();   // S1 consumed
+        if (warp == 0 && next < ntiles) stage_in<VEC>(S1, a.x1, (size_t)next * g.tile_rows, tile_nrows(next), H, g.pitch, &bars[0], lane);
         if (tid == 0) {
             tc_fence_after();
             gemm3<0, 0>(tU, xB, xB + P::PLANE, P::PS, w1B, w1B + P::WPLANE, P::WPS, KP, KP / 16, false);
@@ -579,20 +652,21 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
         mbar_wait(&bars[1], ph_mma, abortf);
         ph_mma ^= 1;
         tc_fence_after();
-#pragma unroll
-        for (int c8 = 0; c8 < KP / 8; ++c8) {
-            float u[8], ks[8];
-            tmem_ld8(tmem_addr(tU, warp, 8 * c8), u);
+#pragma unroll 1
+        for (int c8 = half; c8 < NCH; c8 += kHalves) {
+            float u[8], b[8];
+            tmem_ld8(tmem_addr(tU, qtr, 8 * c8), u);
+            ld8s(cv.c1f + 8 * c8, b);
+            const uint32_t kb = th16 ? keep8(key2, th16, grow, ch8, c8) : 0xffu;
             tmem_wait_ld();
-            if (dr.thresh) drop8(dr, a.site_base + 2, grow, (uint32_t)(ch + 7) >> 3, c8, ks);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = 8 * c8 + j;
-                float gv = act_fwd<ACT>(u[j] + c1f[c]);
-                if (dr.thresh) gv *= ks[j];
+                float gv = act_fwd<ACT>(u[j] + b[j]);
+                gv = (kb >> j) & 1u ? gv * dr.scale : 0.0f;
                 u[j] = !valid ? 0.0f : (c < ch ? gv : (c == ch ? 1.0f : 0.0f));
             }
-            put_chunk(bufY, P::PLANE, P::PS, tid, c8, u);
+            put_chunk(bufY, P::PLANE, P::PS, prow, c8, u);
         }
         fence_async_smem();
         tc_fence_before();
@@ -609,31 +683,32 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
         ph_mma ^= 1;
         tc_fence_after();
         {
-            float v[KP];      // y2, then dY2
-            float dyr[KP];
-            load_row<KP, VEC>(S2 + (size_t)drow * g.pitch, valid ? H : 0, dyr);
             float ssum = 0.0f, dgate = 0.0f;
-#pragma unroll
-            for (int c8 = 0; c8 < KP / 8; ++c8) {
-                float u[8], ks[8];
-                tmem_ld8(tmem_addr(tY, warp, 8 * c8), u);
+            unsigned long long keepbits = 0ull;
+            int i = 0;
+#pragma unroll 1
+            for (int c8 = half; c8 < nchH; c8 += kHalves, ++i) {
+                float u[8], b[8], dyv[8];
+                tmem_ld8(tmem_addr(tY, qtr, 8 * c8), u);
+                ld8s(cv.c2 + 8 * c8, b);
+                ld8<VEC>(drw, 8 * c8, valid ? H : 0, dyv);
+                const uint32_t kb = th16 ? keep8(key3, th16, grow, H8, c8) : 0xffu;
+                keepbits |= (unsigned long long)kb << (8 * i);
                 tmem_wait_ld();
-                if (dr.thresh) drop8(dr, a.site_base + 3, grow, (uint32_t)(H + 7) >> 3, c8, ks);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int h = 8 * c8 + j;
-                    float yv = u[j] + c2[h];
-                    if (dr.thresh) yv *= ks[j];
-                    yv = (valid && h < H) ? yv : 0.0f;
-                    v[h] = yv;
+                    float yv = u[j] + b[j];
+                    yv = (kb >> j) & 1u ? yv * dr.scale : 0.0f;
+                    yv = (valid && 8 * c8 + j < H) ? yv : 0.0f;
                     ssum += yv;
-                    dgate = fmaf(dyr[h], yv, dgate);
+                    dgate = fmaf(dyv[j], yv, dgate);
                 }
             }
+            row_exchange(cv.ex, half, prow, ssum, dgate);
             float gate = 1.0f, dsq = 0.0f;
             if (rr > 0) {
                 const float sq = ssum / (float)H;
-                const SeOut se = se_excite(sq, t, seq_base, T, rr, se1, se2);
+                const SeOut se = se_excite(sq, t, seq_base, T, rr, cv.se1, cv.se2);
                 gate = se.gate;
                 const float dq = valid ? dgate * gate * (1.0f - gate) : 0.0f;
                 float da[kMaxRR];
@@ -643,14 +718,14 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
                     const float dqt = __shfl_sync(0xffffffffu, dq, seq_base + tt);
 #pragma unroll
                     for (int k = 0; k < kMaxRR; ++k)
-                        if (k < rr) da[k] = fmaf(dqt, se2[tt * rr + k], da[k]);
+                        if (k < rr) da[k] = fmaf(dqt, cv.se2[tt * rr + k], da[k]);
                 }
 #pragma unroll
                 for (int k = 0; k < kMaxRR; ++k)
                     if (k < rr) {
                         const float dz = se.z[k] > 0.0f ? da[k] : 0.0f;
-                        dsq = fmaf(dz, se1[k * T + t], dsq);
-                        if (valid) {
+                        dsq = fmaf(dz, cv.se1[k * T + t], dsq);
+                        if (valid && half == 0) {
                             gS2[k] = fmaf(dq, fmaxf(se.z[k], 0.0f), gS2[k]);
                             gS1[k] = fmaf(dz, sq, gS1[k]);
                         }
@@ -658,18 +733,19 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
                 dsq /= (float)H;
             }
             // dY2 = reg2'( dy * gate + dsq )
-#pragma unroll
-            for (int c8 = 0; c8 < KP / 8; ++c8) {
-                float ks[8], o[8];
-                if (dr.thresh) drop8(dr, a.site_base + 3, grow, (uint32_t)(H + 7) >> 3, c8, ks);
+            i = 0;
+#pragma unroll 1
+            for (int c8 = half; c8 < NCH; c8 += kHalves, ++i) {
+                float dyv[8];
+                ld8<VEC>(drw, 8 * c8, valid ? H : 0, dyv);
+                const uint32_t kb = (uint32_t)(keepbits >> (8 * i)) & 0xffu;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int h = 8 * c8 + j;
-                    float d = fmaf(dyr[h], gate, dsq);
-                    if (dr.thresh) d *= ks[j];
-                    o[j] = (valid && h < H) ? d : 0.0f;
+                    float d = fmaf(dyv[j], gate, dsq);
+                    d = (kb >> j) & 1u ? d * dr.scale : 0.0f;
+                    dyv[j] = (valid && 8 * c8 + j < H) ? d : 0.0f;
                 }
-                put_chunk(bufX, P::PLANE, P::PS, tid, c8, o);
+                put_chunk(bufX, P::PLANE, P::PS, prow, c8, dyv);
             }
         }
         fence_async_smem();
@@ -687,25 +763,26 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
         mbar_wait(&bars[1], ph_mma, abortf);
         ph_mma ^= 1;
         tc_fence_after();
-#pragma unroll
-        for (int c8 = 0; c8 < KP / 8; ++c8) {
-            float u[8], dg[8], ks[8];
-            tmem_ld8(tmem_addr(tU, warp, 8 * c8), u);
-            tmem_ld8(tmem_addr(tY, warp, 8 * c8), dg);
+#pragma unroll 1
+        for (int c8 = half; c8 < NCH; c8 += kHalves) {
+            float u[8], dg[8], xh[8], b[8];
+            tmem_ld8(tmem_addr(tU, qtr, 8 * c8), u);
+            tmem_ld8(tmem_addr(tY, qtr, 8 * c8), dg);
+            tmem_ld8(tmem_addr(tXH, qtr, 8 * c8), xh);
+            ld8s(cv.c1f + 8 * c8, b);
+            const uint32_t kb = th16 ? keep8(key2, th16, grow, ch8, c8) : 0xffu;
             tmem_wait_ld();
-            if (dr.thresh) drop8(dr, a.site_base + 2, grow, (uint32_t)(ch + 7) >> 3, c8, ks);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int c = 8 * c8 + j;
                 float av;
-                const float dact = act_fwd_grad<ACT>(u[j] + c1f[c], &av);
+                const float dact = act_fwd_grad<ACT>(u[j] + b[j], &av);
                 float d = dg[j] * dact;
-                if (dr.thresh) d *= ks[j];
-                u[j] = (valid && c < ch) ? d : 0.0f;
+                d = (kb >> j) & 1u ? d * dr.scale : 0.0f;
+                u[j] = (valid && 8 * c8 + j < ch) ? d : 0.0f;
             }
-            put_chunk(bufY, P::PLANE, P::PS, tid, c8, u);
+            put_chunk(bufY, P::PLANE, P::PS, prow, c8, u);
+            put_chunk(bufX, P::PLANE, P::PS, prow, c8, xh);
         }
-        put_row<KP>(bufX, tid, xh);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -723,36 +800,41 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
         ph_mma ^= 1;
         tc_fence_after();
         {
-            float d[KP];
             float m1 = 0.0f, m2 = 0.0f;
-#pragma unroll
-            for (int c8 = 0; c8 < KP / 8; ++c8) {
-                float u[8];
-                tmem_ld8(tmem_addr(tU, warp, 8 * c8), u);
+#pragma unroll 1
+            for (int c8 = half; c8 < nchH; c8 += kHalves) {
+                float u[8], xh[8];
+                tmem_ld8(tmem_addr(tU, qtr, 8 * c8), u);
+                tmem_ld8(tmem_addr(tXH, qtr, 8 * c8), xh);
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int h = 8 * c8 + j;
-                    const float dv = h < H ? u[j] : 0.0f;
-                    d[h] = dv;
+                    const float dv = 8 * c8 + j < H ? u[j] : 0.0f;
                     m1 += dv;
-                    m2 = fmaf(dv, xh[h], m2);
+                    m2 = fmaf(dv, xh[j], m2);
                 }
             }
+            row_exchange(cv.ex, half, prow, m1, m2);
             m1 /= (float)H;
             m2 /= (float)H;
-            float dyr[KP];
-            load_row<KP, VEC>(S2 + (size_t)drow * g.pitch, valid ? H : 0, dyr);
+            float* orow = reinterpret_cast<float*>(bufX) + (size_t)drow * g.pitch;
+#pragma unroll 1
+            for (int c8 = half; c8 < nchH; c8 += kHalves) {
+                float u[8], xh[8], dyv[8];
+                tmem_ld8(tmem_addr(tU, qtr, 8 * c8), u);
+                tmem_ld8(tmem_addr(tXH, qtr, 8 * c8), xh);
+                ld8<VEC>(drw, 8 * c8, valid ? H : 0, dyv);
+                tmem_wait_ld();
 #pragma unroll
-            for (int k = 0; k < KP; ++k) d[k] = fmaf(rstd, d[k] - m1 - xh[k] * m2, dyr[k]);
-            tc_fence_before();
-            if (valid) store_row<KP, VEC>(reinterpret_cast<float*>(bufX) + (size_t)drow * g.pitch, H, d);
+                for (int j = 0; j < 8; ++j) u[j] = fmaf(rstd, u[j] - m1 - xh[j] * m2, dyv[j]);
+                if (valid) st8<VEC>(orow, 8 * c8, H, u);
+            }
         }
+        tc_fence_before();
         fence_async_smem();
         __syncthreads();
         if (warp == 0) {
             stage_out<VEC>(a.out, reinterpret_cast<const float*>(bufX), (size_t)tile * g.tile_rows, nrows, H, g.pitch, lane);
-            store_pending = true;
             if (next < ntiles) stage_in<VEC>(S2, a.dy, (size_t)next * g.tile_rows, tile_nrows(next), H, g.pitch, &bars[2], lane);
         }
     }
@@ -760,25 +842,24 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
     __syncthreads();
 
     // ---------------- flush: Wt, dW2 (TMEM, lane = output row) -> global gradients
-    // thread c (< ch) owns row c of Wt [ch][H | ones]; thread h (< H) owns row h of dW2 [H][ch | ones]
+    // lane c (< ch) holds row c of Wt [ch][H | ones]; lane h (< H) holds row h of dW2 [H][ch | ones]
     if (!first) {
         float* stg = reinterpret_cast<float*>(bufX);          // [KP][KP+1] staging for lane-contiguous REDs
         constexpr int SP = KP + 1;
         tc_fence_after();
-        // Wt
-#pragma unroll
-        for (int c8 = 0; c8 < KP / 8; ++c8) {
+#pragma unroll 1
+        for (int c8 = half; c8 < NCH; c8 += kHalves) {
             float u[8];
-            tmem_ld8(tmem_addr(tDW1, warp, 8 * c8), u);
+            tmem_ld8(tmem_addr(tDW1, qtr, 8 * c8), u);
             tmem_wait_ld();
-            if (tid < KP)
+            if (prow < KP)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) stg[tid * SP + 8 * c8 + j] = u[j];
+                for (int j = 0; j < 8; ++j) stg[prow * SP + 8 * c8 + j] = u[j];
         }
         __syncthreads();
         for (int i = tid; i < ch * H; i += kThreadsChan) {
             const int c = i / H, h = i - c * H;
-            red_add(a.g_w1 + i, stg[c * SP + h] * gam[h]);
+            red_add(a.g_w1 + i, stg[c * SP + h] * cv.gam[h]);
         }
         for (int h = tid; h < H; h += kThreadsChan) {
             float sg = 0.0f, sb = 0.0f;
@@ -792,15 +873,14 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
         }
         for (int c = tid; c < ch; c += kThreadsChan) red_add(a.g_b1 + c, stg[c * SP + H]);
         __syncthreads();
-        // dW2
-#pragma unroll
-        for (int c8 = 0; c8 < KP / 8; ++c8) {
+#pragma unroll 1
+        for (int c8 = half; c8 < NCH; c8 += kHalves) {
             float u[8];
-            tmem_ld8(tmem_addr(tDW2, warp, 8 * c8), u);
+            tmem_ld8(tmem_addr(tDW2, qtr, 8 * c8), u);
             tmem_wait_ld();
-            if (tid < KP)
+            if (prow < KP)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) stg[tid * SP + 8 * c8 + j] = u[j];
+                for (int j = 0; j < 8; ++j) stg[prow * SP + 8 * c8 + j] = u[j];
         }
         __syncthreads();
         for (int i = tid; i < H * ch; i += kThreadsChan) {
@@ -808,13 +888,12 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
             red_add(a.g_w2 + i, stg[h * SP + c]);
         }
         for (int h = tid; h < H; h += kThreadsChan) red_add(a.g_b2 + h, stg[h * SP + ch]);
-        // SE gradients: every valid thread holds partial sums for its frame t
         if (rr > 0) {
             __syncthreads();
             float* acc = stg;                                  // [2][rr*T]
             for (int i = tid; i < 2 * rr * T; i += kThreadsChan) acc[i] = 0.0f;
             __syncthreads();
-            if (lane_ok)
+            if (lane_ok && half == 0)
                 for (int k = 0; k < rr; ++k) {
                     atomicAdd(acc + k * T + t, gS1[k]);              // dS1[k][t]
                     atomicAdd(acc + rr * T + t * rr + k, gS2[k]);    // dS2[t][k]

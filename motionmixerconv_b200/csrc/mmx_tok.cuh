@@ -5,17 +5,21 @@
 //
 // The token MLP contracts over the T frames (K = T and K = tokens_mlp_dim, 10 and 20 in the reference's configurations): far
 // too shallow for a tensor-core tile, so it runs as register FMAs, ONE THREAD PER (sequence, hidden column): the thread holds
-// its column's T frames in registers, both contractions are thread-local, and the weights are warp-uniform broadcast reads
-// from shared memory.  What crosses threads -- LayerNorm statistics, the SE squeeze, the LayerNorm backward sums (all sums over
-// the hidden dim of a (sequence, frame) row) -- goes through the shared tile with one thread per ROW doing the sum.
-// Tiles of S whole sequences enter and leave through the bulk-copy engine (cp.async.bulk + mbarrier).
+// its column's T frames in registers as T/2 packed pairs, both contractions are thread-local packed FMAs (fma.rn.f32x2: the
+// weight rows come out of shared memory as 64-bit pairs, warp-uniform broadcast reads), and the loop over the hidden units
+// j is a rolled loop.  What crosses threads -- LayerNorm statistics, the SE squeeze, the LayerNorm backward sums (all sums
+// over the hidden dim of a (sequence, frame) row) -- goes through the shared tile: every thread sums a slice of a row, one
+// thread per row adds the slices.  Tiles of S whole sequences enter and leave through the bulk-copy engine
+// (cp.async.bulk + mbarrier).
 // Backward: forward recomputed; the token weight gradients (a [tok x T] product whose contraction runs over ALL columns of
 // ALL sequences) are computed from operands staged in shared memory by "owner" threads with register-resident 4x4 accumulator
 // tiles that persist across the CTA's loop over tiles (one flush per CTA).
+// Dropout: one keep-bit stream per column covers both sites of the token MLP (bits [0,tok): after the activation, bits
+// [tok, tok+T): after fc2) -- chan::keep8 with row = b*H + h, W8 = ceil((tok+T)/8), site = site_base.
 #pragma once
 #include "mmx_common.cuh"
 #include "mmx_tc5.cuh"
-#include "mmx_chan_tc5.cuh"   // drop8
+#include "mmx_chan_tc5.cuh"   // keep8 / drop_key
 
 namespace mmx {
 namespace tok {
@@ -23,8 +27,9 @@ namespace tok {
 using namespace tc5;
 
 constexpr int kMaxT = 16;      // frames per sequence served (register arrays)
-constexpr int kMaxTok = 32;    // tokens_mlp_dim served
+constexpr int kMaxTok = 32;    // tokens_mlp_dim served (keep bits of one column fit 64 bits together with the T bits)
 constexpr int kMaxRRt = 4;
+constexpr int kTokThreads = 256;
 
 struct TokArgs {
     const float* x;              // [B,T,H] block input
@@ -33,32 +38,37 @@ struct TokArgs {
     const float *ln_g, *ln_b, *w1, *b1, *w2, *b2, *se1, *se2;
     float *g_ln_g, *g_ln_b, *g_w1, *g_b1, *g_w2, *g_b2, *g_se1, *g_se2;
     int B, T, H, tok, rr;
-    int S;                       // sequences per tile; S*T*H % 4 == 0
-    int site_base;               // token MLP dropout sites: site_base + 0 (after act), + 1 (after fc2)
+    int S;                       // sequences per tile; S*H <= 256, S*T <= 256, T*H % 4 == 0
+    int site_base;
     Dropout dr;
     int* abort_count;
 };
 
 struct TokSmem {                 // offsets in floats
-    int x, d, y, stat, sq, gate, w1, b1, w2, b2, lg, lb, se1, se2, stg, misc, total;
-    int cols_pad, rows;
+    int x, d, y, part, stat, sq, gate, w1, w2t, b1, b2, lg, lb, se1, se2, stg, misc, total;
+    int cols_pad, rows, PR, TPW;
 };
-MMX_HD TokSmem tok_smem(int T, int H, int tok, int S, bool bwd) {
+MMX_HD TokSmem tok_smem(int T, int H, int tok, int S, int TT, bool bwd) {
     TokSmem m;
-    const int tile = (S * T * H + 3) / 4 * 4;
+    const int tile = (S * T * H + 3) / 4 * 4 + 4;
     m.rows = S * T;
+    m.PR = kTokThreads / m.rows < 1 ? 1 : kTokThreads / m.rows;
+    if (m.PR > 8) m.PR = 8;
+    m.TPW = (TT + 3) / 4 * 4;
     m.cols_pad = (S * H + 3) / 4 * 4 + 4;
     int o = 0;
     m.x = o; o += tile;
     m.d = o; o += bwd ? tile : 0;
     m.y = o; o += tile;
+    m.part = o; o += 2 * m.rows * m.PR;
     m.stat = o; o += 2 * m.rows;            // mean, rstd
     m.sq = o; o += 2 * m.rows;              // squeeze / dgate   (bwd: also m1, m2 of the LayerNorm backward)
     m.gate = o; o += 2 * m.rows;            // gate / ds
-    m.w1 = o; o += (tok * T + 3) / 4 * 4;
+    o = (o + 3) / 4 * 4;
+    m.w1 = o; o += tok * m.TPW;             // fc1.weight [tok][T] rows, pitch TPW, zero padded
+    m.w2t = o; o += tok * m.TPW;            // fc2.weight transposed: [tok][T]
     m.b1 = o; o += (tok + 3) / 4 * 4;
-    m.w2 = o; o += (T * tok + 3) / 4 * 4;
-    m.b2 = o; o += (T + 3) / 4 * 4;
+    m.b2 = o; o += m.TPW;
     m.lg = o; o += (H + 3) / 4 * 4;
     m.lb = o; o += (H + 3) / 4 * 4;
     m.se1 = o; o += 32 * kMaxRRt;
@@ -69,95 +79,140 @@ MMX_HD TokSmem tok_smem(int T, int H, int tok, int S, bool bwd) {
     return m;
 }
 
-// sum over the H columns of row `row` of a dense [rows][H] tile (rotated start: conflict-free for any H)
-MMX_D float row_sum(const float* tile, int row, int H) {
-    const float* p = tile + (size_t)row * H;
-    float s = 0.0f;
-    int k = row % H;
-    for (int i = 0; i < H; ++i) { s += p[k]; k = k + 1 == H ? 0 : k + 1; }
-    return s;
-}
+MMX_D float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
-// excitation of one sequence (T squeeze values at sq[0..T)) for frame t; returns the gate and the pre-activations z
-MMX_D float excite(const float* sq, int t, int T, int rr, const float* se1, const float* se2, float (&z)[kMaxRRt]) {
+// excitation of one sequence (T squeeze values at sq[0], sq[stride], ...) for frame t; returns the gate and the pre-activations z
+MMX_D float excite(const float* sq, int stride, int t, int T, int rr, const float* se1, const float* se2, float (&z)[kMaxRRt]) {
     float q = 0.0f;
 #pragma unroll
     for (int k = 0; k < kMaxRRt; ++k) {
         z[k] = 0.0f;
         if (k < rr) {
-            for (int tt = 0; tt < T; ++tt) z[k] = fmaf(se1[k * T + tt], sq[tt], z[k]);
+            for (int tt = 0; tt < T; ++tt) z[k] = fmaf(se1[k * T + tt], sq[tt * stride], z[k]);
             q = fmaf(se2[t * rr + k], fmaxf(z[k], 0.0f), q);
         }
     }
     return sigmoidf_(q);
 }
 
-template <int NW>
 MMX_D void load_params(float* sm, const TokSmem& m, const TokArgs& a, int tid) {
-    const int nt = NW * 32;
-    for (int i = tid; i < a.tok * a.T; i += nt) { sm[m.w1 + i] = a.w1[i]; sm[m.w2 + i] = a.w2[i]; }
-    for (int i = tid; i < a.tok; i += nt) sm[m.b1 + i] = a.b1[i];
-    for (int i = tid; i < a.T; i += nt) sm[m.b2 + i] = a.b2[i];
+    const int nt = kTokThreads, T = a.T, tok = a.tok;
+    for (int i = tid; i < tok * m.TPW; i += nt) {
+        const int j = i / m.TPW, t = i - j * m.TPW;
+        sm[m.w1 + i] = t < T ? a.w1[j * T + t] : 0.0f;
+        sm[m.w2t + i] = t < T ? a.w2[t * tok + j] : 0.0f;
+    }
+    for (int i = tid; i < (tok + 3) / 4 * 4; i += nt) sm[m.b1 + i] = i < tok ? a.b1[i] : 0.0f;
+    for (int i = tid; i < m.TPW; i += nt) sm[m.b2 + i] = i < T ? a.b2[i] : 0.0f;
     for (int i = tid; i < a.H; i += nt) { sm[m.lg + i] = a.ln_g[i]; sm[m.lb + i] = a.ln_b[i]; }
     for (int i = tid; i < 32 * kMaxRRt; i += nt) {
-        sm[m.se1 + i] = (a.rr > 0 && i < a.rr * a.T) ? a.se1[i] : 0.0f;
-        sm[m.se2 + i] = (a.rr > 0 && i < a.rr * a.T) ? a.se2[i] : 0.0f;
+        sm[m.se1 + i] = (a.rr > 0 && i < a.rr * T) ? a.se1[i] : 0.0f;
+        sm[m.se2 + i] = (a.rr > 0 && i < a.rr * T) ? a.se2[i] : 0.0f;
     }
 }
 
-// forward of one column: n[t] (normalised, affine) -> y[t] (token MLP output after reg2).  TT, TOK compile-time bounds.
+// keep bits of one column: bit j (< tok): reg1 element j; bit tok + t: reg2 element t
+MMX_D unsigned long long column_keep(const Dropout& dr, uint32_t key, uint32_t colrow, int tok, int T) {
+    if (!dr.thresh) return ~0ull;
+    const uint32_t n8 = (uint32_t)(tok + T + 7) >> 3;
+    unsigned long long k = 0ull;
+    for (uint32_t c8 = 0; c8 < n8; ++c8) k |= (unsigned long long)chan::keep8(key, dr.thresh >> 16, colrow, n8, c8) << (8 * c8);
+    return k;
+}
+
+// weight row j (TT floats, pitch TPW) as TT/2 packed pairs
+template <int TT>
+MMX_D void load_wrow(const float* p, float2 (&w)[TT / 2]) {
+#pragma unroll
+    for (int i = 0; i + 1 < TT / 2; i += 2) {
+        const float4 v = *reinterpret_cast<const float4*>(p + 2 * i);
+        w[i] = make_float2(v.x, v.y);
+        w[i + 1] = make_float2(v.z, v.w);
+    }
+    if ((TT / 2) & 1) w[TT / 2 - 1] = *reinterpret_cast<const float2*>(p + TT - 2);
+}
+
+// forward of one column: n (normalised, affine) -> y (token MLP output after reg2), packed pairs over t
 template <int ACT, int TT>
-MMX_D void column_fwd(const float* sm, const TokSmem& m, int T, int tok, const float (&n)[TT], float (&y)[TT], const Dropout& dr,
-                      uint32_t site_base, uint32_t colrow) {
+MMX_D void column_fwd(const float* sm, const TokSmem& m, int tok, const float2 (&n)[TT / 2], float2 (&y)[TT / 2], unsigned long long keep,
+                      float scale) {
 #pragma unroll
-    for (int t = 0; t < TT; ++t) y[t] = t < T ? sm[m.b2 + t] : 0.0f;
-    const uint32_t tok8 = (uint32_t)(tok + 7) >> 3;
-    for (int j8 = 0; j8 < (int)tok8; ++j8) {
-        float ks[8];
-        if (dr.thresh) chan::drop8(dr, site_base + 0, colrow, tok8, j8, ks);
+    for (int p = 0; p < TT / 2; ++p) y[p] = *reinterpret_cast<const float2*>(sm + m.b2 + 2 * p);
+#pragma unroll 2
+    for (int j = 0; j < tok; ++j) {
+        float2 w[TT / 2];
+        load_wrow<TT>(sm + m.w1 + j * m.TPW, w);
+        float2 acc = make_float2(sm[m.b1 + j], 0.0f);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const int j = 8 * j8 + jj;
-            if (j < tok) {
-                float u = sm[m.b1 + j];
-                const float* w = sm + m.w1 + j * T;
+        for (int p = 0; p < TT / 2; ++p) acc = ffma2(w[p], n[p], acc);
+        float gv = act_fwd<ACT>(acc.x + acc.y);
+        gv = (keep >> j) & 1ull ? gv * scale : 0.0f;
+        load_wrow<TT>(sm + m.w2t + j * m.TPW, w);
+        const float2 gg = make_float2(gv, gv);
 #pragma unroll
-                for (int t = 0; t < TT; ++t)
-                    if (t < T) u = fmaf(w[t], n[t], u);
-                float gv = act_fwd<ACT>(u);
-                if (dr.thresh) gv *= ks[jj];
-#pragma unroll
-                for (int t = 0; t < TT; ++t)
-                    if (t < T) y[t] = fmaf(sm[m.w2 + t * tok + j], gv, y[t]);
-            }
-        }
+        for (int p = 0; p < TT / 2; ++p) y[p] = ffma2(w[p], gg, y[p]);
     }
-    if (dr.thresh) {
-        const uint32_t t8 = (uint32_t)(T + 7) >> 3;
-        for (int c8 = 0; c8 < (int)t8; ++c8) {
-            float ks[8];
-            chan::drop8(dr, site_base + 1, colrow, t8, c8, ks);
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-                if (8 * c8 + jj < TT) y[8 * c8 + jj] *= ks[jj];
-        }
+    for (int p = 0; p < TT / 2; ++p) {
+        y[p].x = (keep >> (tok + 2 * p)) & 1ull ? y[p].x * scale : 0.0f;
+        y[p].y = (keep >> (tok + 2 * p + 1)) & 1ull ? y[p].y * scale : 0.0f;
     }
+}
+
+// partial sums of every row of a dense [rows][H] tile by all threads: thread -> (row, slice); f(row, h) returns the two
+// addends.  Results land in part[(row * PR + slice) * 2 + {0,1}]; combine with row_total() after a CTA barrier.
+template <class F>
+MMX_D void row_partials(float* sm, const TokSmem& m, int nrows, int H, int tid, F&& f) {
+    const int row = tid / m.PR, sl = tid - row * m.PR;
+    if (row < nrows) {
+        float a = 0.0f, b = 0.0f;
+        for (int h = sl; h < H; h += m.PR) {
+            float u, v;
+            f(row, h, u, v);
+            a += u;
+            b += v;
+        }
+        sm[m.part + (row * m.PR + sl) * 2] = a;
+        sm[m.part + (row * m.PR + sl) * 2 + 1] = b;
+    }
+}
+MMX_D void row_total(const float* sm, const TokSmem& m, int row, float& a, float& b) {
+    a = 0.0f; b = 0.0f;
+    for (int s = 0; s < m.PR; ++s) { a += sm[m.part + (row * m.PR + s) * 2]; b += sm[m.part + (row * m.PR + s) * 2 + 1]; }
+}
+
+// LayerNorm statistics of the x tile (shifted one-pass: the shift is the row's first element).  Two CTA barriers.
+MMX_D void ln_stats(float* sm, const TokSmem& m, int nrows, int H, int tid) {
+    row_partials(sm, m, nrows, H, tid, [&](int r, int h, float& u, float& v) {
+        const float dv = sm[m.x + (size_t)r * H + h] - sm[m.x + (size_t)r * H];
+        u = dv; v = dv * dv;
+    });
+    __syncthreads();
+    if (tid < nrows) {
+        float s, ss;
+        row_total(sm, m, tid, s, ss);
+        const float ms = s / (float)H;
+        sm[m.stat + 2 * tid] = sm[m.x + (size_t)tid * H] + ms;
+        sm[m.stat + 2 * tid + 1] = 1.0f / sqrtf(fmaxf(ss / (float)H - ms * ms, 0.0f) + 1e-5f);
+    }
+    __syncthreads();
 }
 
 // ==========================================================================================
 // forward:  x -> x1
 // ==========================================================================================
-template <int ACT, int TT, int NW>
-__global__ void __launch_bounds__(NW * 32) tok_fwd_kernel(const TokArgs a) {
+template <int ACT, int TT>
+__global__ void __launch_bounds__(kTokThreads) tok_fwd_kernel(const TokArgs a) {
     extern __shared__ float4 tok_smem_raw[];
     float* sm = reinterpret_cast<float*>(tok_smem_raw);
-    const TokSmem m = tok_smem(a.T, a.H, a.tok, a.S, false);
+    const TokSmem m = tok_smem(a.T, a.H, a.tok, a.S, TT, false);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + m.misc);
     volatile int* abortf = reinterpret_cast<volatile int*>(sm + m.misc + 8);
-    const int tid = threadIdx.x, T = a.T, H = a.H, S = a.S, rr = a.rr;
+    const int tid = threadIdx.x, T = a.T, H = a.H, S = a.S, rr = a.rr, tok = a.tok;
     const Dropout dr = resolve_dropout(a.dr);
+    const uint32_t key = chan::drop_key(dr.seed_lo, dr.seed_hi, a.site_base, dr.step);
     if (tid == 0) { mbar_init(&bars[0], 1); *abortf = 0; fence_mbar_init(); }
-    load_params<NW>(sm, m, a, tid);
+    load_params(sm, m, a, tid);
     __syncthreads();
     const int ntiles = (a.B + S - 1) / S;
     const int s_l = tid / H, h = tid - s_l * H;
@@ -173,58 +228,58 @@ __global__ void __launch_bounds__(NW * 32) tok_fwd_kernel(const TokArgs a) {
         const int nrows = nseq * T;
         mbar_wait(&bars[0], ph, abortf);
         ph ^= 1;
-        // ---- A: LayerNorm statistics, one thread per row
-        if (tid < nrows) {
-            const float mean = row_sum(sm + m.x, tid, H) / (float)H;
-            const float* p = sm + m.x + (size_t)tid * H;
-            float ss = 0.0f;
-            int k = tid % H;
-            for (int i = 0; i < H; ++i) { const float dv = p[k] - mean; ss = fmaf(dv, dv, ss); k = k + 1 == H ? 0 : k + 1; }
-            sm[m.stat + 2 * tid] = mean;
-            sm[m.stat + 2 * tid + 1] = 1.0f / sqrtf(ss / (float)H + 1e-5f);
-        }
-        __syncthreads();
-        // ---- B: token MLP of the thread's column
+        ln_stats(sm, m, nrows, H, tid);
+        // ---- token MLP of the thread's column
         const bool act_col = col_ok && s_l < nseq;
-        float x[TT], y[TT];
+        float2 x[TT / 2], y[TT / 2];
         if (act_col) {
-            float n[TT];
+            float2 n[TT / 2];
             const float gmm = sm[m.lg + h], bta = sm[m.lb + h];
 #pragma unroll
             for (int t = 0; t < TT; ++t) {
+                float xv = 0.0f, nv = 0.0f;
                 if (t < T) {
                     const int r = s_l * T + t;
-                    x[t] = sm[m.x + (size_t)r * H + h];
-                    n[t] = fmaf((x[t] - sm[m.stat + 2 * r]) * sm[m.stat + 2 * r + 1], gmm, bta);
-                } else { x[t] = 0.0f; n[t] = 0.0f; }
+                    xv = sm[m.x + (size_t)r * H + h];
+                    nv = fmaf((xv - sm[m.stat + 2 * r]) * sm[m.stat + 2 * r + 1], gmm, bta);
+                }
+                if (t & 1) { x[t / 2].y = xv; n[t / 2].y = nv; } else { x[t / 2].x = xv; n[t / 2].x = nv; }
             }
-            column_fwd<ACT, TT>(sm, m, T, a.tok, n, y, dr, a.site_base, (uint32_t)((size_t)(tile * S + s_l) * H + h));
+            const unsigned long long keep = column_keep(dr, key, (uint32_t)((size_t)(tile * S + s_l) * H + h), tok, T);
+            column_fwd<ACT, TT>(sm, m, tok, n, y, keep, dr.scale);
             if (rr > 0) {
 #pragma unroll
                 for (int t = 0; t < TT; ++t)
-                    if (t < T) sm[m.y + (size_t)(s_l * T + t) * H + h] = y[t];
+                    if (t < T) sm[m.y + (size_t)(s_l * T + t) * H + h] = (t & 1) ? y[t / 2].y : y[t / 2].x;
             }
         }
         if (rr > 0) {
             __syncthreads();
-            // ---- C: squeeze (mean over the hidden dim of every row)
-            if (tid < nrows) sm[m.sq + tid] = row_sum(sm + m.y, tid, H) / (float)H;
+            // ---- squeeze (mean over the hidden dim of every row) and excitation
+            row_partials(sm, m, nrows, H, tid, [&](int r, int hh, float& u, float& v) { u = sm[m.y + (size_t)r * H + hh]; v = 0.0f; });
+            __syncthreads();
+            if (tid < nrows) {
+                float s, dummy;
+                row_total(sm, m, tid, s, dummy);
+                sm[m.sq + 2 * tid] = s / (float)H;
+            }
             __syncthreads();
             if (tid < nrows) {
                 float z[kMaxRRt];
                 const int sq0 = (tid / T) * T;
-                sm[m.gate + tid] = excite(sm + m.sq + sq0, tid - sq0, T, rr, sm + m.se1, sm + m.se2, z);
+                sm[m.gate + 2 * tid] = excite(sm + m.sq + 2 * sq0, 2, tid - sq0, T, rr, sm + m.se1, sm + m.se2, z);
             }
             __syncthreads();
         }
-        // ---- D: gate + residual, in place in the x tile
+        // ---- gate + residual, in place in the x tile
         if (act_col) {
 #pragma unroll
             for (int t = 0; t < TT; ++t)
                 if (t < T) {
                     const int r = s_l * T + t;
-                    const float gte = rr > 0 ? sm[m.gate + r] : 1.0f;
-                    sm[m.x + (size_t)r * H + h] = fmaf(y[t], gte, x[t]);
+                    const float gte = rr > 0 ? sm[m.gate + 2 * r] : 1.0f;
+                    const float yv = (t & 1) ? y[t / 2].y : y[t / 2].x, xv = (t & 1) ? x[t / 2].y : x[t / 2].x;
+                    sm[m.x + (size_t)r * H + h] = fmaf(yv, gte, xv);
                 }
         }
         fence_async_smem();
@@ -249,18 +304,19 @@ __global__ void __launch_bounds__(NW * 32) tok_fwd_kernel(const TokArgs a) {
 // ==========================================================================================
 // backward:  (x, dx1) -> dx, parameter gradients of the token half
 // ==========================================================================================
-template <int ACT, int TT, int NW>
-__global__ void __launch_bounds__(NW * 32) tok_bwd_kernel(const TokArgs a) {
+template <int ACT, int TT>
+__global__ void __launch_bounds__(kTokThreads, 2) tok_bwd_kernel(const TokArgs a) {
     extern __shared__ float4 tok_smem_raw[];
     float* sm = reinterpret_cast<float*>(tok_smem_raw);
-    const TokSmem m = tok_smem(a.T, a.H, a.tok, a.S, true);
+    const TokSmem m = tok_smem(a.T, a.H, a.tok, a.S, TT, true);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + m.misc);
     volatile int* abortf = reinterpret_cast<volatile int*>(sm + m.misc + 8);
-    constexpr int NT = NW * 32;
+    constexpr int NT = kTokThreads;
     const int tid = threadIdx.x, T = a.T, H = a.H, S = a.S, rr = a.rr, tok = a.tok;
     const Dropout dr = resolve_dropout(a.dr);
+    const uint32_t key = chan::drop_key(dr.seed_lo, dr.seed_hi, a.site_base, dr.step);
     if (tid == 0) { mbar_init(&bars[0], 1); *abortf = 0; fence_mbar_init(); }
-    load_params<NW>(sm, m, a, tid);
+    load_params(sm, m, a, tid);
     // staging area: rows [0,T] = N (row T: ones), [T+1, 2T] = DYT, [2T+1, 2T+tok] = DU, [2T+tok+1, 2T+2tok+1] = G (last: ones)
     const int CP = m.cols_pad;
     float* sN = sm + m.stg;
@@ -289,11 +345,11 @@ __global__ void __launch_bounds__(NW * 32) tok_bwd_kernel(const TokArgs a) {
     const float* oA = oprod ? sDYT : sDU;
     const float* oB = oprod ? sG : sN;
     const int oAr = oprod ? T : tok, oBr = oprod ? tok + 1 : T + 1;
-    float acc[4][4];
+    float2 acc[4][4];     // packed partial sums over even / odd columns
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
     float g_lg = 0.0f, g_lb = 0.0f;                  // dLN1.weight[h], dLN1.bias[h] of the thread's column
     float gS1[kMaxRRt], gS2[kMaxRRt];
 #pragma unroll
@@ -311,58 +367,51 @@ __global__ void __launch_bounds__(NW * 32) tok_bwd_kernel(const TokArgs a) {
         const int nrows = nseq * T;
         mbar_wait(&bars[0], ph, abortf);
         ph ^= 1;
-        // ---- A: LayerNorm statistics
-        if (tid < nrows) {
-            const float mean = row_sum(sm + m.x, tid, H) / (float)H;
-            const float* p = sm + m.x + (size_t)tid * H;
-            float ss = 0.0f;
-            int k = tid % H;
-            for (int i = 0; i < H; ++i) { const float dv = p[k] - mean; ss = fmaf(dv, dv, ss); k = k + 1 == H ? 0 : k + 1; }
-            sm[m.stat + 2 * tid] = mean;
-            sm[m.stat + 2 * tid + 1] = 1.0f / sqrtf(ss / (float)H + 1e-5f);
-        }
-        __syncthreads();
-        // ---- B: forward of the column (n, y)
+        ln_stats(sm, m, nrows, H, tid);
+        // ---- forward of the column (n, y)
         const bool act_col = col_ok && s_l < nseq;
-        const uint32_t colrow = (uint32_t)((size_t)(tile * S + s_l) * H + h);
-        float n[TT], xh[TT], dyt[TT];
+        const unsigned long long keep = act_col ? column_keep(dr, key, (uint32_t)((size_t)(tile * S + s_l) * H + h), tok, T) : 0ull;
+        float2 n[TT / 2], xh[TT / 2], dyt[TT / 2];
         const float gmm = col_ok ? sm[m.lg + h] : 0.0f, bta = col_ok ? sm[m.lb + h] : 0.0f;
         if (act_col) {
-            float y[TT];
 #pragma unroll
             for (int t = 0; t < TT; ++t) {
+                float xv = 0.0f, nv = 0.0f;
                 if (t < T) {
                     const int r = s_l * T + t;
-                    xh[t] = (sm[m.x + (size_t)r * H + h] - sm[m.stat + 2 * r]) * sm[m.stat + 2 * r + 1];
-                    n[t] = fmaf(xh[t], gmm, bta);
-                } else { xh[t] = 0.0f; n[t] = 0.0f; }
+                    xv = (sm[m.x + (size_t)r * H + h] - sm[m.stat + 2 * r]) * sm[m.stat + 2 * r + 1];
+                    nv = fmaf(xv, gmm, bta);
+                }
+                if (t & 1) { xh[t / 2].y = xv; n[t / 2].y = nv; } else { xh[t / 2].x = xv; n[t / 2].x = nv; }
             }
             if (rr > 0) {
-                column_fwd<ACT, TT>(sm, m, T, tok, n, y, dr, a.site_base, colrow);
+                float2 y[TT / 2];
+                column_fwd<ACT, TT>(sm, m, tok, n, y, keep, dr.scale);
 #pragma unroll
                 for (int t = 0; t < TT; ++t)
-                    if (t < T) sm[m.y + (size_t)(s_l * T + t) * H + h] = y[t];
+                    if (t < T) sm[m.y + (size_t)(s_l * T + t) * H + h] = (t & 1) ? y[t / 2].y : y[t / 2].x;
             }
         }
         if (rr > 0) {
             __syncthreads();
-            // ---- C: squeeze and d(gate) per row
+            // ---- squeeze and d(gate) per row
+            row_partials(sm, m, nrows, H, tid, [&](int r, int hh, float& u, float& v) {
+                u = sm[m.y + (size_t)r * H + hh];
+                v = u * sm[m.d + (size_t)r * H + hh];
+            });
+            __syncthreads();
             if (tid < nrows) {
-                const float* py = sm + m.y + (size_t)tid * H;
-                const float* pd = sm + m.d + (size_t)tid * H;
-                float s = 0.0f, dg = 0.0f;
-                int k = tid % H;
-                for (int i = 0; i < H; ++i) { s += py[k]; dg = fmaf(pd[k], py[k], dg); k = k + 1 == H ? 0 : k + 1; }
+                float s, dg;
+                row_total(sm, m, tid, s, dg);
                 sm[m.sq + 2 * tid] = s / (float)H;
                 sm[m.sq + 2 * tid + 1] = dg;
             }
             __syncthreads();
-            // ---- C2: excitation forward + backward of the row's sequence
+            // ---- excitation forward + backward of the row's sequence
             if (tid < nrows) {
                 const int sq0 = (tid / T) * T, t = tid - sq0;
-                float sqv[kMaxT], z[kMaxRRt];
-                for (int tt = 0; tt < T; ++tt) sqv[tt] = sm[m.sq + 2 * (sq0 + tt)];
-                const float gate = excite(sqv, t, T, rr, sm + m.se1, sm + m.se2, z);
+                float z[kMaxRRt];
+                const float gate = excite(sm + m.sq + 2 * sq0, 2, t, T, rr, sm + m.se1, sm + m.se2, z);
                 float da[kMaxRRt];
 #pragma unroll
                 for (int k = 0; k < kMaxRRt; ++k) da[k] = 0.0f;
@@ -386,89 +435,71 @@ __global__ void __launch_bounds__(NW * 32) tok_bwd_kernel(const TokArgs a) {
                         const float dz = z[k] > 0.0f ? da[k] : 0.0f;
                         ds = fmaf(dz, sm[m.se1 + k * T + t], ds);
                         gS2[k] = fmaf(dq_own, fmaxf(z[k], 0.0f), gS2[k]);
-                        gS1[k] = fmaf(dz, sqv[t], gS1[k]);
+                        gS1[k] = fmaf(dz, sm[m.sq + 2 * tid], gS1[k]);
                     }
                 sm[m.gate + 2 * tid] = gate;
                 sm[m.gate + 2 * tid + 1] = ds / (float)H;
             }
             __syncthreads();
         }
-        // ---- E: backward of the column
-        float dnh[TT];
+        // ---- backward of the column
+        float2 dnh[TT / 2];
         if (act_col) {
 #pragma unroll
             for (int t = 0; t < TT; ++t) {
+                float v = 0.0f;
                 if (t < T) {
                     const int r = s_l * T + t;
                     const float d1 = sm[m.d + (size_t)r * H + h];
-                    dyt[t] = rr > 0 ? fmaf(d1, sm[m.gate + 2 * r], sm[m.gate + 2 * r + 1]) : d1;
-                } else dyt[t] = 0.0f;
-            }
-            if (dr.thresh) {
-                const uint32_t t8 = (uint32_t)(T + 7) >> 3;
-                for (int c8 = 0; c8 < (int)t8; ++c8) {
-                    float ks[8];
-                    chan::drop8(dr, a.site_base + 1, colrow, t8, c8, ks);
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj)
-                        if (8 * c8 + jj < TT) dyt[8 * c8 + jj] *= ks[jj];
+                    v = rr > 0 ? fmaf(d1, sm[m.gate + 2 * r], sm[m.gate + 2 * r + 1]) : d1;
+                    v = (keep >> (tok + t)) & 1ull ? v * dr.scale : 0.0f;
+                    sDYT[t * CP + tid] = v;
                 }
+                if (t & 1) dyt[t / 2].y = v; else dyt[t / 2].x = v;
             }
-            float dn[TT];
+            float2 dn[TT / 2];
 #pragma unroll
-            for (int t = 0; t < TT; ++t) dn[t] = 0.0f;
-            const uint32_t tok8 = (uint32_t)(tok + 7) >> 3;
-            for (int j8 = 0; j8 < (int)tok8; ++j8) {
-                float ks[8];
-                if (dr.thresh) chan::drop8(dr, a.site_base + 0, colrow, tok8, j8, ks);
+            for (int p = 0; p < TT / 2; ++p) dn[p] = make_float2(0.0f, 0.0f);
+#pragma unroll 2
+            for (int j = 0; j < tok; ++j) {
+                float2 w1r[TT / 2], w2r[TT / 2];
+                load_wrow<TT>(sm + m.w1 + j * m.TPW, w1r);
+                load_wrow<TT>(sm + m.w2t + j * m.TPW, w2r);
+                float2 au = make_float2(sm[m.b1 + j], 0.0f), ag = make_float2(0.0f, 0.0f);
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const int j = 8 * j8 + jj;
-                    if (j < tok) {
-                        float u = sm[m.b1 + j];
-                        const float* w = sm + m.w1 + j * T;
-                        float dgj = 0.0f;
+                for (int p = 0; p < TT / 2; ++p) { au = ffma2(w1r[p], n[p], au); ag = ffma2(w2r[p], dyt[p], ag); }
+                float av;
+                const float dact = act_fwd_grad<ACT>(au.x + au.y, &av);
+                const float ksc = (keep >> j) & 1ull ? dr.scale : 0.0f;
+                const float du = (ag.x + ag.y) * dact * ksc;
+                const float2 dd = make_float2(du, du);
 #pragma unroll
-                        for (int t = 0; t < TT; ++t)
-                            if (t < T) { u = fmaf(w[t], n[t], u); dgj = fmaf(sm[m.w2 + t * tok + j], dyt[t], dgj); }
-                        float av;
-                        const float dact = act_fwd_grad<ACT>(u, &av);
-                        float du = dgj * dact;
-                        if (dr.thresh) { av *= ks[jj]; du *= ks[jj]; }
-#pragma unroll
-                        for (int t = 0; t < TT; ++t)
-                            if (t < T) dn[t] = fmaf(w[t], du, dn[t]);
-                        sDU[j * CP + tid] = du;
-                        sG[j * CP + tid] = av;
-                    }
-                }
+                for (int p = 0; p < TT / 2; ++p) dn[p] = ffma2(w1r[p], dd, dn[p]);
+                sDU[j * CP + tid] = du;
+                sG[j * CP + tid] = av * ksc;
             }
 #pragma unroll
             for (int t = 0; t < TT; ++t)
                 if (t < T) {
-                    sN[t * CP + tid] = n[t];
-                    sDYT[t * CP + tid] = dyt[t];
-                    g_lg = fmaf(dn[t], xh[t], g_lg);
-                    g_lb += dn[t];
-                    dnh[t] = dn[t] * gmm;
-                    sm[m.y + (size_t)(s_l * T + t) * H + h] = dnh[t];
+                    const float nv = (t & 1) ? n[t / 2].y : n[t / 2].x, dv = (t & 1) ? dn[t / 2].y : dn[t / 2].x;
+                    const float xv = (t & 1) ? xh[t / 2].y : xh[t / 2].x;
+                    sN[t * CP + tid] = nv;
+                    g_lg = fmaf(dv, xv, g_lg);
+                    g_lb += dv;
+                    const float dh = dv * gmm;
+                    if (t & 1) dnh[t / 2].y = dh; else dnh[t / 2].x = dh;
+                    sm[m.y + (size_t)(s_l * T + t) * H + h] = dh;
                 }
         } else if (col_ok) {
             for (int j = 0; j < tok; ++j) { sDU[j * CP + tid] = 0.0f; sG[j * CP + tid] = 0.0f; }
             for (int t = 0; t < T; ++t) { sN[t * CP + tid] = 0.0f; sDYT[t * CP + tid] = 0.0f; }
         }
         __syncthreads();
-        // ---- F: LayerNorm backward row sums; weight-gradient tiles
-        if (tid < nrows) {
-            const float* pd = sm + m.y + (size_t)tid * H;
-            const float* px = sm + m.x + (size_t)tid * H;
-            const float mean = sm[m.stat + 2 * tid], rstd = sm[m.stat + 2 * tid + 1];
-            float s1 = 0.0f, s2 = 0.0f;
-            int k = tid % H;
-            for (int i = 0; i < H; ++i) { s1 += pd[k]; s2 = fmaf(pd[k], (px[k] - mean) * rstd, s2); k = k + 1 == H ? 0 : k + 1; }
-            sm[m.sq + 2 * tid] = s1 / (float)H;
-            sm[m.sq + 2 * tid + 1] = s2 / (float)H;
-        }
+        // ---- LayerNorm backward row sums; weight-gradient tiles
+        row_partials(sm, m, nrows, H, tid, [&](int r, int hh, float& u, float& v) {
+            u = sm[m.y + (size_t)r * H + hh];
+            v = u * (sm[m.x + (size_t)r * H + hh] - sm[m.stat + 2 * r]) * sm[m.stat + 2 * r + 1];
+        });
         if (owner) {
             const float* ar[4];
             const float* br[4];
@@ -477,6 +508,7 @@ __global__ void __launch_bounds__(NW * 32) tok_bwd_kernel(const TokArgs a) {
                 ar[i] = oA + (size_t)min(4 * obr + i, oAr - 1) * CP;
                 br[i] = oB + (size_t)min(4 * obc + i, oBr - 1) * CP;
             }
+#pragma unroll 1
             for (int q = oks; q < CP / 4; q += KS) {
                 float4 av[4], bv[4];
 #pragma unroll
@@ -485,23 +517,28 @@ __global__ void __launch_bounds__(NW * 32) tok_bwd_kernel(const TokArgs a) {
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        acc[i][j] = fmaf(av[i].x, bv[j].x, acc[i][j]);
-                        acc[i][j] = fmaf(av[i].y, bv[j].y, acc[i][j]);
-                        acc[i][j] = fmaf(av[i].z, bv[j].z, acc[i][j]);
-                        acc[i][j] = fmaf(av[i].w, bv[j].w, acc[i][j]);
+                        acc[i][j] = ffma2(make_float2(av[i].x, av[i].y), make_float2(bv[j].x, bv[j].y), acc[i][j]);
+                        acc[i][j] = ffma2(make_float2(av[i].z, av[i].w), make_float2(bv[j].z, bv[j].w), acc[i][j]);
                     }
             }
         }
         __syncthreads();
-        // ---- G: dx = dx1 + LN1 backward, in place in the dx1 tile
+        if (tid < nrows) {
+            float s1, s2;
+            row_total(sm, m, tid, s1, s2);
+            sm[m.sq + 2 * tid] = s1 / (float)H;
+            sm[m.sq + 2 * tid + 1] = s2 / (float)H;
+        }
+        __syncthreads();
+        // ---- dx = dx1 + LN1 backward, in place in the dx1 tile
         if (act_col) {
 #pragma unroll
             for (int t = 0; t < TT; ++t)
                 if (t < T) {
                     const int r = s_l * T + t;
                     const float rstd = sm[m.stat + 2 * r + 1];
-                    const float v = rstd * (dnh[t] - sm[m.sq + 2 * r] - xh[t] * sm[m.sq + 2 * r + 1]);
-                    sm[m.d + (size_t)r * H + h] += v;
+                    const float dh = (t & 1) ? dnh[t / 2].y : dnh[t / 2].x, xv = (t & 1) ? xh[t / 2].y : xh[t / 2].x;
+                    sm[m.d + (size_t)r * H + h] += rstd * (dh - sm[m.sq + 2 * r] - xv * sm[m.sq + 2 * r + 1]);
                 }
         }
         fence_async_smem();
@@ -531,8 +568,9 @@ __global__ void __launch_bounds__(NW * 32) tok_bwd_kernel(const TokArgs a) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int r = 4 * obr + i, c = 4 * obc + j;
-                if (oprod == 0) { if (r < tok && c <= T) atomicAdd(red + r * (T + 1) + c, acc[i][j]); }
-                else { if (r < T && c <= tok) atomicAdd(red + n0 + r * (tok + 1) + c, acc[i][j]); }
+                const float v = acc[i][j].x + acc[i][j].y;
+                if (oprod == 0) { if (r < tok && c <= T) atomicAdd(red + r * (T + 1) + c, v); }
+                else { if (r < T && c <= tok) atomicAdd(red + n0 + r * (tok + 1) + c, v); }
             }
     }
     if (col_ok) {
