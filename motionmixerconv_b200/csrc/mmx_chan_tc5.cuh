@@ -35,7 +35,10 @@ namespace chan {
 
 using namespace tc5;
 
-constexpr int kHalves = 2;                     // warps per TMEM lane quarter
+#ifndef MMX_CHAN_HALVES
+#define MMX_CHAN_HALVES 4
+#endif
+constexpr int kHalves = MMX_CHAN_HALVES;        // warps per TMEM lane quarter (they split a row's 8-column chunks)
 constexpr int kThreadsChan = 128 * kHalves;
 constexpr int kMaxRR = 4;                      // SE bottleneck width served (T // r_se)
 
@@ -309,8 +312,9 @@ MMX_D void row_exchange(float* ex, int half, int prow, float& a, float& b) {
     ex[(0 * kHalves + half) * 128 + prow] = a;
     ex[(1 * kHalves + half) * 128 + prow] = b;
     __syncthreads();
-    a = ex[(0 * kHalves + 0) * 128 + prow] + ex[(0 * kHalves + 1) * 128 + prow];
-    b = ex[(1 * kHalves + 0) * 128 + prow] + ex[(1 * kHalves + 1) * 128 + prow];
+    a = 0.0f; b = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kHalves; ++i) { a += ex[(0 * kHalves + i) * 128 + prow]; b += ex[(1 * kHalves + i) * 128 + prow]; }
 }
 
 // common carve-up of the dynamic shared memory
