@@ -84,6 +84,15 @@ int mmx_mlp_block_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, cons
 int mmx_mlp_block_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads,
                       const float* x, const float* dy, float* dx, void* stream);
 
+/* Variant that trades one saved tile for less backward work (used by the autograd Function and TrainStep when available):
+ * the forward also writes x1 = x + SE(token MLP(LN1 x)) [B,T,H] (the input of the block's channel half, mlp_mixer.py:155) and
+ * its SE gates [B,T] (null without SE); the backward then skips the token-half forward and the token-MLP recompute.
+ * mmx_mlp_block_saves: 1 when the kernels serving this descriptor support it (the tcgen05 family), else 0. */
+int mmx_mlp_block_saves(const MmxMlpBlockDesc* d);
+int mmx_mlp_block_fwd_save(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* y, float* x1, float* gate, void* stream);
+int mmx_mlp_block_bwd_saved(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads,
+                            const float* x, const float* x1, const float* gate, const float* dy, float* dx, void* stream);
+
 /* Diagnostics of the tcgen05 / TMEM MixerBlock kernels (precision == MMX_PREC_TF32): number of kernels whose mbarrier waits
  * timed out since the process started (a mis-programmed pipeline ends the kernel instead of hanging the GPU); 0 in a healthy
  * run.  Synchronises the device. */

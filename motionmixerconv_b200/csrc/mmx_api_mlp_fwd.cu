@@ -47,3 +47,25 @@ extern "C" int mmx_mlp_block_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockPara
     }
     return d->act == MMX_ACT_GELU ? dispatch_mlp_fwd<ACT_GELU>(a, grid, smem, stream) : dispatch_mlp_fwd<ACT_MISH>(a, grid, smem, stream);
 }
+
+int mmx_mlp_tc5_fwd_save(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* y, float* x1, float* gate, void* stream);
+int mmx_mlp_tc5_bwd_saved(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads, const float* x,
+                          const float* x1, const float* gate, const float* dy, float* dx, void* stream);
+
+extern "C" int mmx_mlp_block_saves(const MmxMlpBlockDesc* d) { return d && mmx_mlp_tc5_ok(d) ? 1 : 0; }
+
+extern "C" int mmx_mlp_block_fwd_save(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* y, float* x1, float* gate,
+                                      void* stream) {
+    if (!d) return fail(MMX_E_INVALID, "null descriptor");
+    if (!x || !y) return fail(MMX_E_INVALID, "mmx_mlp_block_fwd_save: null tensor");
+    if (!mmx_mlp_tc5_ok(d)) return fail(MMX_E_UNSUPPORTED, "mmx_mlp_block_fwd_save: shape / precision not served by the kernels that save the token-half output (see mmx_mlp_block_saves)");
+    return mmx_mlp_tc5_fwd_save(d, w, x, y, x1, gate, stream);
+}
+
+extern "C" int mmx_mlp_block_bwd_saved(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads, const float* x,
+                                       const float* x1, const float* gate, const float* dy, float* dx, void* stream) {
+    if (!d) return fail(MMX_E_INVALID, "null descriptor");
+    if (!x || !dy || !dx) return fail(MMX_E_INVALID, "mmx_mlp_block_bwd_saved: null tensor");
+    if (!mmx_mlp_tc5_ok(d)) return fail(MMX_E_UNSUPPORTED, "mmx_mlp_block_bwd_saved: shape / precision not served (see mmx_mlp_block_saves)");
+    return mmx_mlp_tc5_bwd_saved(d, w, grads, x, x1, gate, dy, dx, stream);
+}

@@ -14,6 +14,10 @@ int mmx_mlp_tc5_bwd(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, const MmxM
     return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator");
 }
 extern "C" int mmx_tc5_abort_count(void) { return 0; }
+int mmx_mlp_tc5_fwd_save(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, const float*, float*, float*, float*, void*) { return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator"); }
+int mmx_mlp_tc5_bwd_saved(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, const MmxMlpBlockParams*, const float*, const float*, const float*, const float*, float*, void*) {
+    return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator");
+}
 #else
 #include <mutex>
 
@@ -104,6 +108,7 @@ static void fill_tok(tok::TokArgs& t, const MmxMlpBlockDesc* d, const MmxMlpBloc
         t.g_ln_g = t.g_ln_b = t.g_w1 = t.g_b1 = t.g_w2 = t.g_b2 = t.g_se1 = t.g_se2 = nullptr;
     }
     t.B = d->B; t.T = d->T; t.H = d->H; t.tok = d->tok; t.rr = d->use_se ? d->se_hidden : 0;
+    t.gate_out = nullptr; t.x1s = nullptr; t.gates = nullptr;
     t.S = S; t.site_base = d->block_index * 4;
     t.dr = make_dropout(d->dropout, d->training);
     t.abort_count = abort_ptr();
@@ -197,6 +202,43 @@ int mmx_mlp_tc5_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const 
     fill_chan(c, d, w, nullptr);
     c.x1 = y; c.dy = nullptr; c.out = y;
     return chan_dispatch(false, d, c, stream);
+}
+
+// forward that also saves the token-half output x1 [B,T,H] and its SE gates [B,T] (gate may be null without SE) for
+// mmx_mlp_tc5_bwd_saved, which then neither re-runs the token half forward nor recomputes the token MLP output
+int mmx_mlp_tc5_fwd_save(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* y, float* x1, float* gate, void* stream) {
+    int rc = check_common(d, w, "mmx_mlp_block_fwd_save");
+    if (rc) return rc;
+    if (!x1 || (d->use_se && !gate)) return fail(MMX_E_INVALID, "mmx_mlp_block_fwd_save: null save buffer");
+    if ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)x1)) & 15) return fail(MMX_E_INVALID, "mmx_mlp_block_fwd_save: tensors must be 16-byte aligned");
+    const int S = tok_S(d);
+    tok::TokArgs t;
+    fill_tok(t, d, w, nullptr, S);
+    t.x = x; t.dx1 = nullptr; t.out = x1; t.gate_out = d->use_se ? gate : nullptr;
+    if ((rc = tok_dispatch(false, d, t, stream))) return rc;
+    chan::ChanArgs c;
+    fill_chan(c, d, w, nullptr);
+    c.x1 = x1; c.dy = nullptr; c.out = y;
+    return chan_dispatch(false, d, c, stream);
+}
+
+int mmx_mlp_tc5_bwd_saved(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads, const float* x,
+                          const float* x1, const float* gate, const float* dy, float* dx, void* stream) {
+    int rc = check_common(d, w, "mmx_mlp_block_bwd_saved");
+    if (rc) return rc;
+    if ((rc = check_common(d, grads, "mmx_mlp_block_bwd_saved(grads)"))) return rc;
+    if (!x1 || (d->use_se && !gate)) return fail(MMX_E_INVALID, "mmx_mlp_block_bwd_saved: null saved tensor");
+    if ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dx) | ((uintptr_t)x1)) & 15) return fail(MMX_E_INVALID, "mmx_mlp_block_bwd_saved: tensors must be 16-byte aligned");
+    if (dx == dy || dx == x || dx == x1) return fail(MMX_E_INVALID, "mmx_mlp_block_bwd_saved: dx must not alias an input");
+    chan::ChanArgs c;
+    fill_chan(c, d, w, grads);
+    c.x1 = x1; c.dy = dy; c.out = dx;
+    if ((rc = chan_dispatch(true, d, c, stream))) return rc;
+    const int S = tok_S(d);
+    tok::TokArgs t;
+    fill_tok(t, d, w, grads, S);
+    t.x = x; t.dx1 = dx; t.out = dx; t.x1s = x1; t.gates = d->use_se ? gate : nullptr;
+    return tok_dispatch(true, d, t, stream);
 }
 
 int mmx_mlp_tc5_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads, const float* x,

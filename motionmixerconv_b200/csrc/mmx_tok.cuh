@@ -35,6 +35,9 @@ struct TokArgs {
     const float* x;              // [B,T,H] block input
     const float* dx1;            // backward: gradient wrt x1 (output of the token half) [B,T,H]
     float* out;                  // forward: x1; backward: dx
+    float* gate_out;             // forward, nullable: SE gates [B,T] saved for the backward
+    const float* x1s;            // backward, nullable: x1 saved by the forward; then `gates` holds its SE gates and the token MLP
+    const float* gates;          //   output is recovered as y = (x1 - x) / gate instead of being recomputed
     const float *ln_g, *ln_b, *w1, *b1, *w2, *b2, *se1, *se2;
     float *g_ln_g, *g_ln_b, *g_w1, *g_b1, *g_w2, *g_b2, *g_se1, *g_se2;
     int B, T, H, tok, rr;
@@ -273,7 +276,9 @@ __global__ void __launch_bounds__(kTokThreads) tok_fwd_kernel(const TokArgs a) {
             if (tid < nrows) {
                 float z[kMaxRRt];
                 const int sq0 = (tid / T) * T;
-                sm[m.gate + 2 * tid] = excite(sm + m.sq + 2 * sq0, 2, tid - sq0, T, rr, sm + m.se1, sm + m.se2, z);
+                const float gte = excite(sm + m.sq + 2 * sq0, 2, tid - sq0, T, rr, sm + m.se1, sm + m.se2, z);
+                sm[m.gate + 2 * tid] = gte;
+                if (a.gate_out) a.gate_out[(size_t)tile * S * T + tid] = gte;
             }
             __syncthreads();
         }
@@ -364,16 +369,22 @@ __global__ void __launch_bounds__(kTokThreads, 2) tok_bwd_kernel(const TokArgs a
 
     uint32_t ph = 0;
     auto tile_bytes = [&](int tile) { return (uint32_t)(min(S, a.B - tile * S) * T * H) * 4u; };
+    const bool saved = a.x1s != nullptr && rr > 0;      // y recovered from the saved x1 (needed for the SE backward only)
     if (tid == 0 && (int)blockIdx.x < ntiles) {
-        mbar_expect_tx(&bars[0], 2 * tile_bytes(blockIdx.x));
+        mbar_expect_tx(&bars[0], (saved ? 3 : 2) * tile_bytes(blockIdx.x));
         bulk_g2s(sm + m.x, a.x + (size_t)blockIdx.x * S * T * H, tile_bytes(blockIdx.x), &bars[0]);
         bulk_g2s(sm + m.d, a.dx1 + (size_t)blockIdx.x * S * T * H, tile_bytes(blockIdx.x), &bars[0]);
+        if (saved) bulk_g2s(sm + m.y, a.x1s + (size_t)blockIdx.x * S * T * H, tile_bytes(blockIdx.x), &bars[0]);
     }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nseq = min(S, a.B - tile * S);
         const int nrows = nseq * T;
         mbar_wait(&bars[0], ph, abortf);
         ph ^= 1;
+        if (saved && tid < nrows) {                     // 1 / gate of every row (read by the squeeze pass below)
+            const float gte = a.gates[(size_t)tile * S * T + tid];
+            sm[m.sq + 2 * tid + 1] = gte > 1e-30f ? 1.0f / gte : 0.0f;
+        }
         ln_stats(sm, m, nrows, H, tid);
         // ---- forward of the column (n, y)
         const bool act_col = col_ok && s_l < nseq;
@@ -392,7 +403,7 @@ __global__ void __launch_bounds__(kTokThreads, 2) tok_bwd_kernel(const TokArgs a
                 }
                 if (t & 1) { xh[t / 2].y = xv; n[t / 2].y = nv; } else { xh[t / 2].x = xv; n[t / 2].x = nv; }
             }
-            if (rr > 0) {
+            if (rr > 0 && !saved) {
                 float2 y[TT / 2];
                 column_fwd<ACT, TT>(sm, m, tok, n, y, keep, dr.scale);
 #pragma unroll
@@ -404,8 +415,13 @@ __global__ void __launch_bounds__(kTokThreads, 2) tok_bwd_kernel(const TokArgs a
             __syncthreads();
             // ---- squeeze and d(gate) per row
             row_partials(sm, m, nrows, H, tid, [&](int r, int hh, float& u, float& v) {
-                const float2 yv = *reinterpret_cast<const float2*>(sm + m.y + r * H + hh);
+                float2 yv = *reinterpret_cast<const float2*>(sm + m.y + r * H + hh);
                 const float2 dv = *reinterpret_cast<const float2*>(sm + m.d + r * H + hh);
+                if (saved) {                            // the y tile holds x1:  y = (x1 - x) / gate
+                    const float2 xv = *reinterpret_cast<const float2*>(sm + m.x + r * H + hh);
+                    const float ig = sm[m.sq + 2 * r + 1];
+                    yv.x = (yv.x - xv.x) * ig; yv.y = (yv.y - xv.y) * ig;
+                }
                 u = yv.x + yv.y; v = fmaf(yv.x, dv.x, yv.y * dv.y);
             });
             __syncthreads();
@@ -562,9 +578,10 @@ __global__ void __launch_bounds__(kTokThreads, 2) tok_bwd_kernel(const TokArgs a
             const int next = tile + gridDim.x;
             bulk_wait_read0();
             if (next < ntiles) {
-                mbar_expect_tx(&bars[0], 2 * tile_bytes(next));
+                mbar_expect_tx(&bars[0], (saved ? 3 : 2) * tile_bytes(next));
                 bulk_g2s(sm + m.x, a.x + (size_t)next * S * T * H, tile_bytes(next), &bars[0]);
                 bulk_g2s(sm + m.d, a.dx1 + (size_t)next * S * T * H, tile_bytes(next), &bars[0]);
+                if (saved) bulk_g2s(sm + m.y, a.x1s + (size_t)next * S * T * H, tile_bytes(next), &bars[0]);
             }
         }
     }

@@ -128,9 +128,19 @@ class _MlpBlock(torch.autograd.Function):
         B, T, H = x.shape
         desc = mlp_block_desc(B, T, H, *meta)
         y = torch.empty_like(x)
+        needs_grad = any(ctx.needs_input_grad)
+        # the tcgen05 kernel family can hand the token-half output (+ SE gates) to the backward: one extra saved tile per
+        # block instead of re-running the token half forward
+        ctx.saved_x1 = bool(needs_grad and L.load().mmx_mlp_block_saves(C.byref(desc)))
         with torch.cuda.device_of(x):
-            _call("mmx_mlp_block_fwd", C.byref(desc), C.byref(mlp_block_table(params)), _p(x), _p(y), _stream())
-        ctx.save_for_backward(x, *[q for q in params if q is not None])
+            if ctx.saved_x1:
+                x1 = torch.empty_like(x)
+                gate = torch.empty(B, T, dtype=x.dtype, device=x.device)
+                _call("mmx_mlp_block_fwd_save", C.byref(desc), C.byref(mlp_block_table(params)), _p(x), _p(y), _p(x1), _p(gate), _stream())
+                ctx.save_for_backward(x, x1, gate, *[q for q in params if q is not None])
+            else:
+                _call("mmx_mlp_block_fwd", C.byref(desc), C.byref(mlp_block_table(params)), _p(x), _p(y), _stream())
+                ctx.save_for_backward(x, *[q for q in params if q is not None])
         ctx.has = [q is not None for q in params]
         ctx.meta = meta
         return y
@@ -138,6 +148,9 @@ class _MlpBlock(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, *rest = ctx.saved_tensors
+        x1 = gate = None
+        if ctx.saved_x1:
+            x1, gate, *rest = rest
         it = iter(rest)
         params = [next(it) if h else None for h in ctx.has]
         dy = _chk(dy, "grad")
@@ -146,8 +159,12 @@ class _MlpBlock(torch.autograd.Function):
         grads = _zeros_like_many(params)
         dx = torch.empty_like(x)
         with torch.cuda.device_of(x):
-            _call("mmx_mlp_block_bwd", C.byref(desc), C.byref(mlp_block_table(params)), C.byref(mlp_block_table(grads)),
-                  _p(x), _p(dy), _p(dx), _stream())
+            if ctx.saved_x1:
+                _call("mmx_mlp_block_bwd_saved", C.byref(desc), C.byref(mlp_block_table(params)), C.byref(mlp_block_table(grads)),
+                      _p(x), _p(x1), _p(gate), _p(dy), _p(dx), _stream())
+            else:
+                _call("mmx_mlp_block_bwd", C.byref(desc), C.byref(mlp_block_table(params)), C.byref(mlp_block_table(grads)),
+                      _p(x), _p(dy), _p(dx), _stream())
         return (dx, None, *grads)
 
 

@@ -97,6 +97,11 @@ class _MlpMixerPlan:
         self.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
         self.n_launches_fwd = 2 + model.num_blocks
         self.n_launches_bwd = 2 + model.num_blocks
+        # kernels that can save the token-half output x1 (+ SE gates) for the backward (the tcgen05 family): one extra tile per block
+        lib = L.load()
+        self.saves = [bool(lib.mmx_mlp_block_saves(C.byref(self._desc(mb, True)))) for mb, _, _ in self.blocks]
+        self.x1 = [torch.empty(B, T, H, device=dev) if s else None for s in self.saves]
+        self.gate = [torch.empty(B, T, device=dev) if s else None for s in self.saves]
 
     def _desc(self, mb, training):
         m = mb.meta(self.seed, 0)
@@ -109,7 +114,11 @@ class _MlpMixerPlan:
         L.check(lib, lib.mmx_linear_fwd(self.B * T, D, H, _p(self.x), _p(self.conv_w), _p(self.conv_b), _p(self.acts[0]), st), "mmx_linear_fwd")
         for i, (mb, tw, _) in enumerate(self.blocks):
             d = self._desc(mb, training)
-            L.check(lib, lib.mmx_mlp_block_fwd(C.byref(d), C.byref(tw), _p(self.acts[i]), _p(self.acts[i + 1]), st), "mmx_mlp_block_fwd")
+            if training and self.saves[i]:
+                L.check(lib, lib.mmx_mlp_block_fwd_save(C.byref(d), C.byref(tw), _p(self.acts[i]), _p(self.acts[i + 1]), _p(self.x1[i]),
+                                                        _p(self.gate[i]), st), "mmx_mlp_block_fwd_save")
+            else:
+                L.check(lib, lib.mmx_mlp_block_fwd(C.byref(d), C.byref(tw), _p(self.acts[i]), _p(self.acts[i + 1]), st), "mmx_mlp_block_fwd")
         L.check(lib, lib.mmx_mlp_head_fwd(C.byref(self.head_desc), C.byref(self.head_w), _p(self.acts[-1]), _p(self.pred), st), "mmx_mlp_head_fwd")
         return self.pred
 
@@ -123,7 +132,11 @@ class _MlpMixerPlan:
             mb, tw, tg = self.blocks[i]
             nxt = self.dact[1] if cur is self.dact[0] else self.dact[0]
             d = self._desc(mb, True)
-            L.check(lib, lib.mmx_mlp_block_bwd(C.byref(d), C.byref(tw), C.byref(tg), _p(self.acts[i]), _p(cur), _p(nxt), st), "mmx_mlp_block_bwd")
+            if self.saves[i]:
+                L.check(lib, lib.mmx_mlp_block_bwd_saved(C.byref(d), C.byref(tw), C.byref(tg), _p(self.acts[i]), _p(self.x1[i]), _p(self.gate[i]),
+                                                         _p(cur), _p(nxt), st), "mmx_mlp_block_bwd_saved")
+            else:
+                L.check(lib, lib.mmx_mlp_block_bwd(C.byref(d), C.byref(tw), C.byref(tg), _p(self.acts[i]), _p(cur), _p(nxt), st), "mmx_mlp_block_bwd")
             cur = nxt
         L.check(lib, lib.mmx_linear_bwd(self.B * T, D, H, _p(self.x), _p(self.conv_w), _p(cur), _p(self.conv_gw), _p(self.conv_gb), None, st), "mmx_linear_bwd")
 
