@@ -42,8 +42,12 @@ extern "C" {
 int mmx_version(void);
 const char* mmx_last_error(void);
 
-/* Dropout (nn.Dropout sites inside the blocks; mlp_mixer.py:68-70, conv_mixer_model.py:113-114).
- * Masks are Philox4x32-10(key = seed, counter = (element/4, 0.., site, step + *step_dev)); p == 0 disables. */
+/* Dropout (nn.Dropout sites inside the blocks; mlp_mixer.py:68-70, conv_mixer_model.py:113-114).  p == 0 disables.  Masks are a
+ * pure function of (seed, site, step + *step_dev, element); the generator depends on the kernel family serving the shape
+ * (tests/masks_np.py holds bit-exact numpy twins of all of them):
+ *   generic MixerBlock / ConvMixer kernels: Philox4x32-10, one 32-bit word per element;
+ *   warp-per-sequence-pair MixerBlock kernels: Philox4x32-7, 16 bits per element;
+ *   tcgen05 MixerBlock kernels: lowbias32 counter hash, 16 bits per element. */
 typedef struct {
     float p;
     unsigned long long seed;
@@ -97,6 +101,11 @@ int mmx_mlp_block_bwd_saved(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w
  * timed out since the process started (a mis-programmed pipeline ends the kernel instead of hanging the GPU); 0 in a healthy
  * run.  Synchronises the device. */
 int mmx_tc5_abort_count(void);
+/* Test / debug: the keep-scales (0 or 1/(1-p)) the tcgen05 MixerBlock kernels draw for dropout site `site` seen as a
+ * [rows][W] tensor (d->step_dev is ignored).  Channel MLP: site 4*block+2 on [B*T][ch], 4*block+3 on [B*T][H]; token MLP: ONE
+ * stream per (sequence, hidden column), site 4*block on [B*H][tok+T] (columns [0,tok): after the activation, the rest: after fc2).
+ * tests/masks_np.py holds the numpy twin. */
+int mmx_tc5_dropout_mask(const MmxDropout* d, unsigned int site, long long rows, int W, float* out, void* stream);
 
 /* y[r,:] = W x[r,:] + b  — MlpMixer.conv (Conv2d(1,H,(1,D)) == per-frame Linear, mlp_mixer.py:268,325-327)
  * and PoseEncoder.embed_mlp without harmonics (positional_encoder.py:91).  x:[rows,K] w:[N,K] y:[rows,N]. */

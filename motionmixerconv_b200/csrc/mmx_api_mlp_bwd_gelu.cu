@@ -12,9 +12,6 @@ MMX_DECL_BWD(mmx_mlp_bwd_launch_mish_wt1); MMX_DECL_BWD(mmx_mlp_bwd_launch_mish_
 bool mmx_mlp_tc5_ok(const MmxMlpBlockDesc* d);
 int mmx_mlp_tc5_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads,
                     const float* x, const float* dy, float* dx, void* stream);
-bool mmx_mlp_tc_ok(const MmxMlpBlockDesc* d);
-int mmx_mlp_tc_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads,
-                   const float* x, const float* dy, float* dx, void* stream);
 
 extern "C" int mmx_mlp_block_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads,
                                  const float* x, const float* dy, float* dx, void* stream) {
@@ -23,7 +20,6 @@ extern "C" int mmx_mlp_block_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockPara
     size_t smem; int grid, nwarp = 0;
     if (!d) return fail(MMX_E_INVALID, "null descriptor");
     if (mmx_mlp_tc5_ok(d)) return mmx_mlp_tc5_bwd(d, w, grads, x, dy, dx, stream);   // tcgen05 / TMEM family (sm_100a)
-    if (mmx_mlp_tc_ok(d)) return mmx_mlp_tc_bwd(d, w, grads, x, dy, dx, stream);
     const bool warp_variant = mlp_warp_variant_ok(d);
     int rc = warp_variant ? plan_mlp_block_warp(d, true, &a.d, &smem, &grid, &nwarp) : plan_mlp_block(d, true, &a.d, &smem, &grid);
     if (rc) return rc;

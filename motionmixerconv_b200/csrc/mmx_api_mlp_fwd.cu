@@ -20,8 +20,6 @@ using namespace mmx_tu_mlp_fwd;
 
 bool mmx_mlp_tc5_ok(const MmxMlpBlockDesc* d);
 int mmx_mlp_tc5_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* y, void* stream);
-bool mmx_mlp_tc_ok(const MmxMlpBlockDesc* d);
-int mmx_mlp_tc_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* y, void* stream);
 
 extern "C" int mmx_mlp_block_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* y, void* stream) {
     if (!x || !y) return fail(MMX_E_INVALID, "mmx_mlp_block_fwd: null tensor");
@@ -29,7 +27,6 @@ extern "C" int mmx_mlp_block_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockPara
     size_t smem; int grid, nwarp = 0;
     if (!d) return fail(MMX_E_INVALID, "null descriptor");
     if (mmx_mlp_tc5_ok(d)) return mmx_mlp_tc5_fwd(d, w, x, y, stream);   // tcgen05 / TMEM family (sm_100a)
-    if (mmx_mlp_tc_ok(d)) return mmx_mlp_tc_fwd(d, w, x, y, stream);
     const bool warp_variant = mlp_warp_variant_ok(d);
     int rc = warp_variant ? plan_mlp_block_warp(d, false, &a.d, &smem, &grid, &nwarp) : plan_mlp_block(d, false, &a.d, &smem, &grid);
     if (rc) return rc;

@@ -14,6 +14,7 @@ int mmx_mlp_tc5_bwd(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, const MmxM
     return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator");
 }
 extern "C" int mmx_tc5_abort_count(void) { return 0; }
+extern "C" int mmx_tc5_dropout_mask(const MmxDropout*, unsigned int, long long, int, float*, void*) { return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator"); }
 int mmx_mlp_tc5_fwd_save(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, const float*, float*, float*, float*, void*) { return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator"); }
 int mmx_mlp_tc5_bwd_saved(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, const MmxMlpBlockParams*, const float*, const float*, const float*, const float*, float*, void*) {
     return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator");
@@ -46,6 +47,24 @@ extern "C" int mmx_tc5_abort_count(void) {
     int v = 0;
     cudaMemcpy(&v, abort_ptr(), sizeof(int), cudaMemcpyDeviceToHost);
     return v;
+}
+
+// keep-scales of one dropout site of this kernel family, as the kernels draw them (debug / test entry point)
+static __global__ void tc5_mask_kernel(Dropout dr, uint32_t site, long long rows, int W, float* out) {
+    const uint32_t key = chan::drop_key(dr.seed_lo, dr.seed_hi, site, dr.step), W8 = (uint32_t)(W + 7) >> 3;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows * W; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t row = (uint32_t)(i / W), w = (uint32_t)(i - (long long)row * W);
+        const uint32_t kb = dr.thresh >> 16 ? chan::keep8(key, dr.thresh >> 16, row, W8, w >> 3) : 0xffu;
+        out[i] = (kb >> (w & 7)) & 1u ? dr.scale : 0.0f;
+    }
+}
+extern "C" int mmx_tc5_dropout_mask(const MmxDropout* d, unsigned int site, long long rows, int W, float* out, void* stream) {
+    if (!d || !out || rows <= 0 || W <= 0) return fail(MMX_E_INVALID, "mmx_tc5_dropout_mask: bad argument");
+    const Dropout dr = make_dropout(*d, 1);
+    tc5_mask_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(dr, site, rows, W, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(MMX_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+    return MMX_OK;
 }
 
 static int kp_of(const MmxMlpBlockDesc* d) {

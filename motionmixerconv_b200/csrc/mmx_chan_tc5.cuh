@@ -379,6 +379,11 @@ __global__ void __launch_bounds__(kThreadsChan) chan_fwd_kernel(const ChanArgs a
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc<TM_COLS>(cv.tslot);
+    __syncthreads();           // barriers initialised: the first tile can fly in while the weights are staged
+    const int ntiles = (a.B + g.seq_per_tile - 1) / g.seq_per_tile;
+    auto tile_nrows = [&](int tile) { return min(g.seq_per_tile, a.B - tile * g.seq_per_tile) * a.T; };
+    if (warp == 0 && (int)blockIdx.x < ntiles)
+        stage_in<VEC>(S, a.x1, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), a.H, g.pitch, &bars[0], lane);
     prologue<KP>(a, cv.w1b, cv.w2b, cv.c1f, cv.c2, cv.gam, cv.se1, cv.se2, tid);
     fence_async_smem();
     tc_fence_before();
@@ -388,7 +393,6 @@ __global__ void __launch_bounds__(kThreadsChan) chan_fwd_kernel(const ChanArgs a
     const uint32_t tU = tmem, tY = tmem + KP, tXR = tmem + 2 * KP;
     const uint32_t xB = smem_u32(bufX), w1B = smem_u32(cv.w1b), w2B = smem_u32(cv.w2b);
 
-    const int ntiles = (a.B + g.seq_per_tile - 1) / g.seq_per_tile;
     const bool lane_ok = lane < g.rpw;
     const int t = lane_ok ? lane % T : 0;
     const int seq_base = lane_ok ? (lane / T) * T : 0;
@@ -396,10 +400,6 @@ __global__ void __launch_bounds__(kThreadsChan) chan_fwd_kernel(const ChanArgs a
     const int nchH = (H + 7) >> 3;
     const uint32_t ch8 = (uint32_t)(ch + 7) >> 3, H8 = (uint32_t)nchH;
     uint32_t ph_in = 0, ph_mma = 0;
-
-    auto tile_nrows = [&](int tile) { return min(g.seq_per_tile, a.B - tile * g.seq_per_tile) * T; };
-    if (warp == 0 && (int)blockIdx.x < ntiles)
-        stage_in<VEC>(S, a.x1, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), H, g.pitch, &bars[0], lane);
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nrows = tile_nrows(tile);
@@ -567,6 +567,13 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc<TM_COLS>(cv.tslot);
+    __syncthreads();           // barriers initialised: the first tiles can fly in while the weights are staged
+    const int ntiles = (a.B + g.seq_per_tile - 1) / g.seq_per_tile;
+    auto tile_nrows = [&](int tile) { return min(g.seq_per_tile, a.B - tile * g.seq_per_tile) * a.T; };
+    if (warp == 0 && (int)blockIdx.x < ntiles) {
+        stage_in<VEC>(S1, a.x1, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), a.H, g.pitch, &bars[0], lane);
+        stage_in<VEC>(S2, a.dy, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), a.H, g.pitch, &bars[2], lane);
+    }
     prologue<KP>(a, cv.w1b, cv.w2b, cv.c1f, cv.c2, cv.gam, cv.se1, cv.se2, tid);
     fence_async_smem();
     tc_fence_before();
@@ -577,7 +584,6 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
     const uint32_t tU = tmem, tY = tmem + KP, tXH = tmem + 2 * KP, tDW1 = tmem + 3 * KP, tDW2 = tmem + 4 * KP;
     const uint32_t xB = smem_u32(bufX), yB = smem_u32(bufY), w1B = smem_u32(cv.w1b), w2B = smem_u32(cv.w2b);
 
-    const int ntiles = (a.B + g.seq_per_tile - 1) / g.seq_per_tile;
     const bool lane_ok = lane < g.rpw;
     const int t = lane_ok ? lane % T : 0;
     const int seq_base = lane_ok ? (lane / T) * T : 0;
@@ -590,11 +596,6 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
 #pragma unroll
     for (int k = 0; k < kMaxRR; ++k) gS1[k] = gS2[k] = 0.0f;
 
-    auto tile_nrows = [&](int tile) { return min(g.seq_per_tile, a.B - tile * g.seq_per_tile) * T; };
-    if (warp == 0 && (int)blockIdx.x < ntiles) {
-        stage_in<VEC>(S1, a.x1, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), H, g.pitch, &bars[0], lane);
-        stage_in<VEC>(S2, a.dy, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), H, g.pitch, &bars[2], lane);
-    }
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nrows = tile_nrows(tile);
@@ -867,6 +868,7 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
         }
         for (int h = tid; h < H; h += kThreadsChan) {
             float sg = 0.0f, sb = 0.0f;
+#pragma unroll 8
             for (int c = 0; c < ch; ++c) {
                 const float w = a.w1[(size_t)c * H + h];
                 sg = fmaf(stg[c * SP + h], w, sg);

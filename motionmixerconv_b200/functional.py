@@ -62,7 +62,7 @@ class _Linear(torch.autograd.Function):
         with torch.cuda.device_of(x):
             _call("mmx_linear_fwd", rows, K, N, _p(x), _p(w), _p(b), _p(y), _stream())
         ctx.save_for_backward(x, w)
-        ctx.need_dx = x.requires_grad
+        ctx.need_dx = ctx.needs_input_grad[0]      # not x.requires_grad: _chk may have returned a contiguous copy made under no_grad
         ctx.wshape = w.shape
         return y
 
@@ -230,7 +230,7 @@ class _Mpjpe(torch.autograd.Function):
             raise RuntimeError("mpjpe_error: shapes %s / %s are not matching [*, 3] joint arrays" % (tuple(pred.shape), tuple(gt.shape)))
         n = pred.numel() // 3
         loss_sum = torch.zeros(1, dtype=torch.float32, device=pred.device)
-        dpred = torch.empty_like(pred) if pred.requires_grad else None
+        dpred = torch.empty_like(pred) if ctx.needs_input_grad[0] else None
         with torch.cuda.device_of(pred):
             _call("mmx_mpjpe_fwd_bwd", _p(pred), _p(gt), _p(dpred), _p(loss_sum), n, 1.0, _stream())
         ctx.save_for_backward(dpred)
@@ -480,7 +480,7 @@ class _PoseEncoder(torch.autograd.Function):
             _call("mmx_pose_encoder_fwd", C_.byref(desc), C_.byref(encoder_table([freq, w, b, wc, bc])), _p(x), _p(m), _p(y), _stream())
         ctx.save_for_backward(x, m, w, b, wc, bc, *([freq] if n_harmonic > 0 else []))
         ctx.dims = (B, T, D, E, C, n_harmonic)
-        ctx.need_dx = x.requires_grad
+        ctx.need_dx = ctx.needs_input_grad[0]
         return y
 
     @staticmethod

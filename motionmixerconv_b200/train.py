@@ -252,14 +252,18 @@ class _ConvMixerPlan:
                                               _p(cur), _p(self.dm), None, st), "mmx_pose_encoder_bwd")
 
 
-def _make_plan(model, flat, B, step_dev):
+def _make_plan(model, flat, B, step_dev, rank=0):
     from .mlp_mixer import MlpMixer
     from .conv_mixer_model import ConvMixer
     if isinstance(model, MlpMixer):
-        return _MlpMixerPlan(model, flat, B, step_dev)
-    if isinstance(model, ConvMixer):
-        return _ConvMixerPlan(model, flat, B, step_dev)
-    raise TypeError("TrainStep supports motionmixerconv_b200 MlpMixer / ConvMixer, got %s" % type(model).__name__)
+        plan = _MlpMixerPlan(model, flat, B, step_dev)
+    elif isinstance(model, ConvMixer):
+        plan = _ConvMixerPlan(model, flat, B, step_dev)
+    else:
+        raise TypeError("TrainStep supports motionmixerconv_b200 MlpMixer / ConvMixer, got %s" % type(model).__name__)
+    # data parallel: every rank draws its own dropout masks (identical seeds would give every shard the same masks)
+    plan.seed = (plan.seed + 0x9E3779B97F4A7C15 * rank) & 0xFFFFFFFFFFFFFFFF
+    return plan
 
 
 class TrainStep:
@@ -292,7 +296,15 @@ class TrainStep:
         self.plan = None
         self.gt = None
         self.graph_a = self.graph_b = None
+        self._plans = {}              # batch size -> (plan, gt, graph_a, graph_b): train / eval at different batch sizes do not evict each other
         self.kernel_launches_per_step = 0
+        self.rank = dist.get_rank(process_group) if process_group is not None else 0
+        if self.world > 1:
+            # replicas must start identical (what DDP does at construction): rank 0's parameters and buffers win
+            src = dist.get_global_rank(process_group, 0)
+            dist.broadcast(self.flat.p, src=src, group=process_group)
+            for b in model.buffers():
+                dist.broadcast(b, src=src, group=process_group)
         self._staged, self._copy_stream = None, None      # double-buffered host->device prefetch (step(..., prefetch=...))
 
     # ---- pieces -------------------------------------------------------------------------------
@@ -301,7 +313,7 @@ class TrainStep:
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         self.flat.g.zero_()
         self.loss_sum.zero_()
-        pred = pl.forward(lib, st, training=self.model.training)
+        pred = pl.forward(lib, st, training=True)
         n_joints = pred.numel() // 3
         L.check(lib, lib.mmx_mpjpe_fwd_bwd(_p(pred), _p(self.gt), _p(pl.dpred), _p(self.loss_sum), n_joints,
                                            float(self.loss_scale), st), "mmx_mpjpe_fwd_bwd")
@@ -313,13 +325,28 @@ class TrainStep:
         L.check(self.lib, self.lib.mmx_adam_advance(_p(self.hyper), _p(self.step_dev), st), "mmx_adam_advance")
         L.check(self.lib, self.lib.mmx_adam_step(_p(f.p), _p(f.g), _p(f.m), _p(f.v), f.numel, _p(self.hyper), st), "mmx_adam_step")
 
+    def _select_plan(self, B):
+        """Make the plan (static activations, pointer tables, captured graphs) of batch size B current."""
+        if self.plan is not None and self.plan.B == B:
+            return
+        if self.plan is not None:
+            self._plans[self.plan.B] = (self.plan, self.gt, self.graph_a, self.graph_b)
+        if B in self._plans:
+            self.plan, self.gt, self.graph_a, self.graph_b = self._plans[B]
+        else:
+            self.plan = _make_plan(self.model, self.flat, B, self.step_dev, self.rank)
+            self.gt, self.graph_a, self.graph_b = None, None, None
+        self.kernel_launches_per_step = self.plan.n_launches_fwd + self.plan.n_launches_bwd + 3  # + mpjpe, adam_advance, adam
+
     def _prepare(self, x, gt):
-        B = x.shape[0]
-        if self.plan is None or self.plan.B != B:
-            self.plan = _make_plan(self.model, self.flat, B, self.step_dev)
-            self.gt = torch.empty_like(gt, device=self.device)
-            self.graph_a = self.graph_b = None
-            self.kernel_launches_per_step = self.plan.n_launches_fwd + self.plan.n_launches_bwd + 3  # + mpjpe, adam_advance, adam
+        self._select_plan(x.shape[0])
+        if tuple(x.shape) != tuple(self.plan.x.shape):
+            raise RuntimeError("TrainStep: input %s does not match the model's [B, %d, %d]" % (tuple(x.shape), *self.plan.x.shape[1:]))
+        if self.gt is None or tuple(self.gt.shape) != tuple(gt.shape):
+            if tuple(gt.shape[1:]) != tuple(self.plan.pred.shape[1:]) or gt.shape[0] != x.shape[0]:
+                raise RuntimeError("TrainStep: target %s does not match the prediction %s" % (tuple(gt.shape), tuple(self.plan.pred.shape)))
+            self.gt = torch.empty(gt.shape, dtype=torch.float32, device=self.device)
+            self.graph_a = self.graph_b = None       # the captured step reads the target buffer
 
     def set_lr(self, lr):
         """Change the learning rate (e.g. from a MultiStepLR schedule, train_mixer_h36m.py:65-67,249)."""
@@ -340,6 +367,8 @@ class TrainStep:
         stream now, overlapping this step's kernels (what ``DataLoader(pin_memory=True)`` + ``.to(device, non_blocking=True)``
         gives the reference loop, train_mixer_h36m.py:95-96,111).  The next ``step`` call recognises the same tensors and
         only pays a device-to-device copy."""
+        if not self.model.training:
+            raise RuntimeError("TrainStep.step: the model is in eval() mode (use predict() for inference, model.train() to train)")
         self._prepare(x, gt)
         pl = self.plan
         cur = torch.cuda.current_stream(self.device)
@@ -372,6 +401,10 @@ class TrainStep:
         st["x_src"], st["gt_src"] = x_next, gt_next
 
     def _run_step(self):
+        with torch.cuda.device(self.device):
+            return self._run_step_on_device()
+
+    def _run_step_on_device(self):
         pl = self.plan
         if not self.use_graph:
             self._fwd_bwd()
@@ -394,8 +427,13 @@ class TrainStep:
         writing into the step's static input buffers (no intermediate tensors)."""
         B = batch.shape[0]
         D = len(dim_used)
-        if self.plan is None or self.plan.B != B:
-            self._prepare(torch.empty(B, input_n, D, device=self.device), torch.empty(B, output_n, D, device=self.device))
+        if batch.dim() != 3 or batch.shape[1] < input_n + output_n:
+            raise RuntimeError("step_raw: batch %s holds fewer than input_n + output_n = %d frames" % (tuple(batch.shape), input_n + output_n))
+        idx = torch.as_tensor(dim_used)
+        if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= batch.shape[2]):
+            raise IndexError("step_raw: dim_used index out of range for a batch with %d dims" % batch.shape[2])
+        # shapes are validated against the model by _prepare (static buffers are never written past their end)
+        self._prepare(torch.empty(B, input_n, D, device="meta"), torch.empty(B, output_n, D, device="meta"))
         if not isinstance(dim_used, torch.Tensor) or dim_used.device != self.device or dim_used.dtype != torch.int32:
             dim_used = torch.as_tensor(dim_used, dtype=torch.int32).to(self.device)
         F_.window_split(batch.to(self.device, non_blocking=True), dim_used, input_n, output_n, x_scale, gt_scale,
@@ -426,10 +464,13 @@ class TrainStep:
     @torch.no_grad()
     def predict(self, x):
         """Inference forward through the same preallocated plan (eval semantics: no dropout)."""
-        self._prepare(x, torch.empty(x.shape[0], 1, 3, device=self.device) if self.gt is None else self.gt)
-        self.plan.x.copy_(x, non_blocking=True)
-        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        return self.plan.forward(self.lib, st, training=False)
+        self._select_plan(x.shape[0])            # never touches the target buffer / captured graphs of the training plan
+        if tuple(x.shape) != tuple(self.plan.x.shape):
+            raise RuntimeError("TrainStep.predict: input %s does not match the model's [B, %d, %d]" % (tuple(x.shape), *self.plan.x.shape[1:]))
+        with torch.cuda.device(self.device):
+            self.plan.x.copy_(x, non_blocking=True)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            return self.plan.forward(self.lib, st, training=False)
 
 
 class FusedAdam(torch.optim.Optimizer):

@@ -43,6 +43,14 @@ def rel_err(a, b):
     return float(np.abs(a - b).max()) / denom
 
 
+REPORT = []          # one record per check_close call; tests/conftest.py writes it to profiles/parity_report.json after a GPU run
+
+
+def _record(name, rel, rtol, clause, scale):
+    REPORT.append({"test": os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0], "tensor": name, "rel_err": rel, "rtol": rtol,
+                   "passed_by": clause, "want_absmax": scale})
+
+
 def check_close(name, got, want, truth=None, rtol=1e-5, noise_k=4.0, atol=0.0):
     """Noise-aware form of the north-star criterion.  Passes when EITHER
 
@@ -61,15 +69,22 @@ def check_close(name, got, want, truth=None, rtol=1e-5, noise_k=4.0, atol=0.0):
     assert np.isfinite(got).all(), "%s: non-finite values" % name
     scale = max(float(np.abs(want).max()), 1e-30)
     err = float(np.abs(got - want).max())
+    if err <= rtol * scale:
+        _record(name, err / scale, rtol, "plain relative bar", scale)
+        return err / scale
     if err <= rtol * scale + atol:
+        _record(name, err / scale, rtol, "absolute floor (atol %.3g)" % atol, scale)
         return err / scale
     if truth is not None:
         truth = np.asarray(truth, dtype=np.float64)
         noise = float(np.abs(want - truth).max())
         if float(np.abs(got - truth).max()) <= noise_k * noise + atol:
+            _record(name, err / scale, rtol, "noise clause (reference fp32 vs fp64 noise %.3g rel)" % (noise / scale), scale)
             return err / scale
+        _record(name, err / scale, rtol, "FAILED", scale)
         raise AssertionError("%s: rel err %.3e > %.1e (|want|max %.3e, err %.3e, ref noise %.3e)"
                              % (name, err / scale, rtol, scale, err, noise))
+    _record(name, err / scale, rtol, "FAILED", scale)
     raise AssertionError("%s: rel err %.3e > %.1e (|want|max %.3e)" % (name, err / scale, rtol, scale))
 
 

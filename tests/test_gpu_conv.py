@@ -60,7 +60,8 @@ def test_golden(case):
     check_close("pred_eval", pe, g.pred_eval, rtol=TOL)
 
 
-@pytest.mark.parametrize("case,B", [("conv_k1", 333), ("conv_k3", 37), ("conv_evenk", 65), ("conv_once_se", 70), ("conv_harm64", 130)])
+@pytest.mark.parametrize("case,B", [("conv_k1", 333), ("conv_k3", 37), ("conv_evenk", 65), ("conv_once_se", 70), ("conv_harm64", 130),
+                                    ("conv_k1", 4096)])      # the last: several tiles per CTA of every kernel at a bench-sized batch
 def test_vs_oracle_ragged_batch(case, B):
     """Batch sizes that are not multiples of the CTA tile: several tiles per CTA + a partial last tile."""
     g = Golden(case)

@@ -30,7 +30,7 @@ def _run(model, x, gt):
     loss.backward()
     torch.cuda.synchronize()
     grads = {k: p.grad.detach().cpu().numpy() for k, p in model.named_parameters()}
-    return pred.detach().cpu().numpy(), float(loss), grads, xg.grad.cpu().numpy()
+    return pred.detach().cpu().numpy(), float(loss.detach()), grads, xg.grad.cpu().numpy()
 
 
 MLP_CASES = [c for c in golden_cases("mlp") if c != "mlp_bn"]
@@ -63,6 +63,33 @@ def test_vs_oracle_ragged_batch(case, B):
     g = Golden(case)
     c = g.cfg
     x, gt = synthetic_pose_windows(B, c["seq_len"], c["pred_len"], c["input_size"], scale="amass", seed=7)
+    model = _model(c, g.params).train()
+    pred, loss, grads, dx = _run(model, x, gt)
+    res = {}
+    for dt in (np.float32, np.float64):
+        o = O.MlpMixerOracle(c, g.params, dtype=dt)
+        p = o.forward(x)
+        l, dp = O.mpjpe(p, gt.astype(dt))
+        gr, dxx = o.backward(dp)
+        res[dt] = (p, l, gr, dxx)
+    p32, l32, g32, dx32 = res[np.float32]
+    p64, l64, g64, dx64 = res[np.float64]
+    check_close("pred", pred, p32, p64, rtol=TOL)
+    assert abs(loss - float(l64)) <= TOL * abs(float(l64))
+    floor = 1e-6 * grad_scale(g32)
+    for k in g32:
+        check_close("grad " + k, grads[k], g32[k], g64[k], rtol=TOL, atol=floor)
+    check_close("dx", dx, dx32, dx64, rtol=TOL, atol=1e-6 * float(np.abs(dx32).max()))
+
+
+@pytest.mark.parametrize("case,B", [("mlp_k2", 4096), ("mlp_k2", 4097), ("mlp_k4", 4096)])
+def test_vs_oracle_at_the_benchmark_batch(case, B):
+    """FP32 mode against the numpy oracle (fp32 + fp64) AT the benchmark size: every warp of the persistent kernels runs
+    several loop iterations, the shared-memory accumulator locks are contended, the re-alignment barriers are live
+    (B = 4097: plus a ragged last group)."""
+    g = Golden(case)
+    c = dict(g.cfg, regularization=0)
+    x, gt = synthetic_pose_windows(B, c["seq_len"], c["pred_len"], c["input_size"], scale="h36m" if case == "mlp_k2" else "amass", seed=13)
     model = _model(c, g.params).train()
     pred, loss, grads, dx = _run(model, x, gt)
     res = {}

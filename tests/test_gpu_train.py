@@ -120,3 +120,31 @@ def test_prefetch_pipeline_gives_identical_results():
                 losses.append(float(ts.step(*data[i % 4], prefetch=data[(i + 1) % 4])))
         out.append(losses)
     np.testing.assert_allclose(out[0], out[1], rtol=1e-6)
+
+
+def test_predict_and_step_interleave_at_different_batch_sizes():
+    """predict() before / between step() calls, at the training batch size and at another one, must neither break
+    the target buffer of the training plan nor throw away its captured graphs."""
+    from motionmixerconv_b200.train import TrainStep
+    g = Golden("mlp_k2")
+    cfg = dict(g.cfg, regularization=0)
+    ts = TrainStep(_model(cfg, g.params), lr=1e-3, weight_decay=1e-5)
+    ref = TrainStep(_model(cfg, g.params), lr=1e-3, weight_decay=1e-5)
+    x, gt = torch.from_numpy(g.x).cuda(), torch.from_numpy(g.gt).cuda()
+    x3 = x[:3].contiguous()
+    p0 = ts.predict(x).clone()                       # predict first: no target buffer yet
+    np.testing.assert_allclose(p0.cpu().numpy(), g.pred_eval, rtol=0, atol=1e-5 * np.abs(g.pred_eval).max())
+    l1, r1 = float(ts.step(x, gt)), float(ref.step(x, gt))
+    graph = ts.graph_a
+    p3 = ts.predict(x3)                              # another batch size: a second plan, the first one stays
+    assert p3.shape[0] == 3
+    l2, r2 = float(ts.step(x, gt)), float(ref.step(x, gt))
+    assert ts.graph_a is graph                       # the training plan's captured graphs survived
+    assert (l1, l2) == (r1, r2)
+    assert ts.predict(x).shape == p0.shape
+    with pytest.raises(RuntimeError):
+        ts.model.eval()
+        ts.step(x, gt)
+    ts.model.train()
+    with pytest.raises(RuntimeError):
+        ts.step(x[:, :9], gt)                        # wrong frame count: rejected on the host, no out-of-bounds device write

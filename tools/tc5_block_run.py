@@ -13,8 +13,14 @@ params = [torch.randn(*s, device="cuda") * 0.1 for s in shapes]; grads = [torch.
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 desc = F_.mlp_block_desc(B, T, H, tok, ch, 1, act, True, False, True, 0, p, 1234, 0, prec)
 tw, tg = F_.mlp_block_table(params), F_.mlp_block_table(grads)
+x1 = torch.empty_like(x); gate = torch.empty(B, T, device="cuda")
+save = bool(lib.mmx_mlp_block_saves(C.byref(desc))) and not int(os.environ.get("NOSAVE", 0))
 for _ in range(int(os.environ.get("ITERS", 3))):
-    L.check(lib, lib.mmx_mlp_block_fwd(C.byref(desc), C.byref(tw), x.data_ptr(), y.data_ptr(), st), "fwd")
-    L.check(lib, lib.mmx_mlp_block_bwd(C.byref(desc), C.byref(tw), C.byref(tg), x.data_ptr(), dy.data_ptr(), dx.data_ptr(), st), "bwd")
+    if save:
+        L.check(lib, lib.mmx_mlp_block_fwd_save(C.byref(desc), C.byref(tw), x.data_ptr(), y.data_ptr(), x1.data_ptr(), gate.data_ptr(), st), "fwd")
+        L.check(lib, lib.mmx_mlp_block_bwd_saved(C.byref(desc), C.byref(tw), C.byref(tg), x.data_ptr(), x1.data_ptr(), gate.data_ptr(), dy.data_ptr(), dx.data_ptr(), st), "bwd")
+    else:
+        L.check(lib, lib.mmx_mlp_block_fwd(C.byref(desc), C.byref(tw), x.data_ptr(), y.data_ptr(), st), "fwd")
+        L.check(lib, lib.mmx_mlp_block_bwd(C.byref(desc), C.byref(tw), C.byref(tg), x.data_ptr(), dy.data_ptr(), dx.data_ptr(), st), "bwd")
 torch.cuda.synchronize()
 print("ok abort", lib.mmx_tc5_abort_count())
