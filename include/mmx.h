@@ -97,6 +97,18 @@ int mmx_mlp_block_fwd_save(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w,
 int mmx_mlp_block_bwd_saved(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads,
                             const float* x, const float* x1, const float* gate, const float* dy, float* dx, void* stream);
 
+/* The two halves of a MixerBlock as the tcgen05 family runs them (MMX_E_UNSUPPORTED when mmx_mlp_block_saves(d) == 0):
+ *   token half   (mlp_mixer.py:146-155)  x1 = x + SE(token MLP(LN1 x)^T)^T          fp32 CUDA cores (packed fma.rn.f32x2)
+ *   channel half (mlp_mixer.py:157-164)  y  = x1 + SE(channel MLP(LN2 x1))          tcgen05.mma, accumulators in TMEM
+ * token_half_bwd: x1 / gate nullable (then the token MLP output is recomputed); dx may alias dx1.  channel_half_bwd: dx1 may
+ * alias x1.  Gradients accumulated. */
+int mmx_mlp_token_half_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* x1, float* gate, void* stream);
+int mmx_mlp_token_half_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads, const float* x,
+                           const float* x1, const float* gate, const float* dx1, float* dx, void* stream);
+int mmx_mlp_channel_half_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x1, float* y, void* stream);
+int mmx_mlp_channel_half_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads, const float* x1,
+                             const float* dy, float* dx1, void* stream);
+
 /* Diagnostics of the tcgen05 / TMEM MixerBlock kernels (precision == MMX_PREC_TF32): number of kernels whose mbarrier waits
  * timed out since the process started (a mis-programmed pipeline ends the kernel instead of hanging the GPU); 0 in a healthy
  * run.  Synchronises the device. */

@@ -78,6 +78,10 @@ SIGNATURES = {
     "mmx_mlp_block_bwd": (C.c_int, [C.POINTER(MmxMlpBlockDesc), C.POINTER(MmxMlpBlockParams), C.POINTER(MmxMlpBlockParams),
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_tc5_abort_count": (C.c_int, []),
+    "mmx_mlp_token_half_fwd": (C.c_int, [C.POINTER(MmxMlpBlockDesc), C.POINTER(MmxMlpBlockParams)] + [C.c_void_p] * 4),
+    "mmx_mlp_token_half_bwd": (C.c_int, [C.POINTER(MmxMlpBlockDesc), C.POINTER(MmxMlpBlockParams), C.POINTER(MmxMlpBlockParams)] + [C.c_void_p] * 6),
+    "mmx_mlp_channel_half_fwd": (C.c_int, [C.POINTER(MmxMlpBlockDesc), C.POINTER(MmxMlpBlockParams)] + [C.c_void_p] * 3),
+    "mmx_mlp_channel_half_bwd": (C.c_int, [C.POINTER(MmxMlpBlockDesc), C.POINTER(MmxMlpBlockParams), C.POINTER(MmxMlpBlockParams)] + [C.c_void_p] * 4),
     "mmx_tc5_dropout_mask": (C.c_int, [C.POINTER(MmxDropout), C.c_uint, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "mmx_mlp_block_saves": (C.c_int, [C.POINTER(MmxMlpBlockDesc)]),
     "mmx_mlp_block_fwd_save": (C.c_int, [C.POINTER(MmxMlpBlockDesc), C.POINTER(MmxMlpBlockParams)] + [C.c_void_p] * 5),

@@ -280,3 +280,58 @@ int mmx_mlp_tc5_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const 
     return tok_dispatch(true, d, t, stream);
 }
 #endif
+
+// ------------------------------------------------------------------------------------------ the two halves as entry points
+// (what mmx_mlp_block_{fwd,bwd}[_save[d]] are made of; used by the benchmark to time the dominant kernel on its own)
+#if !defined(MMX_HOST_EMU)
+extern "C" int mmx_mlp_token_half_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x, float* x1, float* gate, void* stream) {
+    if (!d || !mmx_mlp_tc5_ok(d)) return fail(MMX_E_UNSUPPORTED, "mmx_mlp_token_half_fwd: shape / precision not served by the tcgen05 family");
+    int rc = check_common(d, w, "mmx_mlp_token_half_fwd");
+    if (rc) return rc;
+    if (!x || !x1) return fail(MMX_E_INVALID, "mmx_mlp_token_half_fwd: null tensor");
+    tok::TokArgs t;
+    fill_tok(t, d, w, nullptr, tok_S(d));
+    t.x = x; t.out = x1; t.gate_out = d->use_se ? gate : nullptr;
+    return tok_dispatch(false, d, t, stream);
+}
+extern "C" int mmx_mlp_token_half_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads, const float* x,
+                                      const float* x1, const float* gate, const float* dx1, float* dx, void* stream) {
+    if (!d || !mmx_mlp_tc5_ok(d)) return fail(MMX_E_UNSUPPORTED, "mmx_mlp_token_half_bwd: shape / precision not served by the tcgen05 family");
+    int rc = check_common(d, w, "mmx_mlp_token_half_bwd");
+    if (rc) return rc;
+    if ((rc = check_common(d, grads, "mmx_mlp_token_half_bwd(grads)"))) return rc;
+    if (!x || !dx1 || !dx) return fail(MMX_E_INVALID, "mmx_mlp_token_half_bwd: null tensor");
+    tok::TokArgs t;
+    fill_tok(t, d, w, grads, tok_S(d));
+    t.x = x; t.dx1 = dx1; t.out = dx; t.x1s = x1; t.gates = (x1 && d->use_se) ? gate : nullptr;
+    if (t.x1s && d->use_se && !t.gates) return fail(MMX_E_INVALID, "mmx_mlp_token_half_bwd: saved x1 without its gates");
+    return tok_dispatch(true, d, t, stream);
+}
+extern "C" int mmx_mlp_channel_half_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const float* x1, float* y, void* stream) {
+    if (!d || !mmx_mlp_tc5_ok(d)) return fail(MMX_E_UNSUPPORTED, "mmx_mlp_channel_half_fwd: shape / precision not served by the tcgen05 family");
+    int rc = check_common(d, w, "mmx_mlp_channel_half_fwd");
+    if (rc) return rc;
+    if (!x1 || !y) return fail(MMX_E_INVALID, "mmx_mlp_channel_half_fwd: null tensor");
+    chan::ChanArgs c;
+    fill_chan(c, d, w, nullptr);
+    c.x1 = x1; c.dy = nullptr; c.out = y;
+    return chan_dispatch(false, d, c, stream);
+}
+extern "C" int mmx_mlp_channel_half_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads, const float* x1,
+                                        const float* dy, float* dx1, void* stream) {
+    if (!d || !mmx_mlp_tc5_ok(d)) return fail(MMX_E_UNSUPPORTED, "mmx_mlp_channel_half_bwd: shape / precision not served by the tcgen05 family");
+    int rc = check_common(d, w, "mmx_mlp_channel_half_bwd");
+    if (rc) return rc;
+    if ((rc = check_common(d, grads, "mmx_mlp_channel_half_bwd(grads)"))) return rc;
+    if (!x1 || !dy || !dx1) return fail(MMX_E_INVALID, "mmx_mlp_channel_half_bwd: null tensor");
+    chan::ChanArgs c;
+    fill_chan(c, d, w, grads);
+    c.x1 = x1; c.dy = dy; c.out = dx1;
+    return chan_dispatch(true, d, c, stream);
+}
+#else
+extern "C" int mmx_mlp_token_half_fwd(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, const float*, float*, float*, void*) { return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator"); }
+extern "C" int mmx_mlp_token_half_bwd(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, const MmxMlpBlockParams*, const float*, const float*, const float*, const float*, float*, void*) { return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator"); }
+extern "C" int mmx_mlp_channel_half_fwd(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, const float*, float*, void*) { return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator"); }
+extern "C" int mmx_mlp_channel_half_bwd(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, const MmxMlpBlockParams*, const float*, const float*, float*, void*) { return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator"); }
+#endif

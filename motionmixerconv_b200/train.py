@@ -102,6 +102,8 @@ class _MlpMixerPlan:
         self.saves = [bool(lib.mmx_mlp_block_saves(C.byref(self._desc(mb, True)))) for mb, _, _ in self.blocks]
         self.x1 = [torch.empty(B, T, H, device=dev) if s else None for s in self.saves]
         self.gate = [torch.empty(B, T, device=dev) if s else None for s in self.saves]
+        self.n_launches_fwd = 2 + sum(2 if s else 1 for s in self.saves)      # tcgen05 family: token half + channel half
+        self.n_launches_bwd = 2 + sum(2 if s else 1 for s in self.saves)
 
     def _desc(self, mb, training):
         m = mb.meta(self.seed, 0)
@@ -415,9 +417,10 @@ class TrainStep:
             if self.graph_a is None:
                 self._capture()
             self.graph_a.replay()
-            if self.world > 1:
-                P_.allreduce_bucket(self.flat.g, self.pg)
-            self.graph_b.replay()
+            if self.graph_b is not None:          # two-graph form: eager all-reduce between backward and Adam
+                if self.world > 1:
+                    P_.allreduce_bucket(self.flat.g, self.pg)
+                self.graph_b.replay()
         n_joints = pl.pred.numel() // 3
         return (self.loss_sum * (float(self.loss_scale) / n_joints)).reshape(())
 
@@ -448,18 +451,32 @@ class TrainStep:
         saved = [b.clone() for b in state]
         with torch.cuda.stream(s):
             self._fwd_bwd()
+            if self.world > 1:
+                P_.allreduce_bucket(self.flat.g, self.pg)      # also initialises the NCCL communicator before any capture
             self._adam()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize(self.device)
         with torch.no_grad():
             for b, sv in zip(state, saved):
                 b.copy_(sv)
+        import os
+        one_graph = self.world == 1 or os.environ.get("MMX_DP_GRAPH_ALLREDUCE", "1") != "0"
         self.graph_a = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_a):
-            self._fwd_bwd()
-        self.graph_b = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_b):
-            self._adam()
+        if one_graph:
+            # ONE graph per step: forward, backward, the NCCL all-reduce of the flat gradient bucket (NCCL collectives are
+            # capturable) and the fused Adam -- no host round trip between backward, the collective and the optimizer
+            with torch.cuda.graph(self.graph_a):
+                self._fwd_bwd()
+                if self.world > 1:
+                    P_.allreduce_bucket(self.flat.g, self.pg)
+                self._adam()
+            self.graph_b = None
+        else:
+            with torch.cuda.graph(self.graph_a):
+                self._fwd_bwd()
+            self.graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_b):
+                self._adam()
 
     @torch.no_grad()
     def predict(self, x):
