@@ -444,9 +444,21 @@ def run_ours(args, w):
             roof["tensor_tflops_issued"] = tensor_flops / (t_k * 1e-3) / 1e12
         roof.update(others)
 
+    def shutdown():
+        """Tear the process group down without ever blocking the benchmark's exit (the JSON line is already out)."""
+        if world <= 1:
+            return
+        ts.release_graphs()
+        if alt:
+            ts2.release_graphs()
+        killer = threading.Timer(20.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
+        dist.destroy_process_group()
+        killer.cancel()
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
     c = w["cfg"]
     x0, g0 = host[0]
@@ -487,8 +499,7 @@ def run_ours(args, w):
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(w)
     emit(out)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():

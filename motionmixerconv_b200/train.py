@@ -350,6 +350,16 @@ class TrainStep:
             self.gt = torch.empty(gt.shape, dtype=torch.float32, device=self.device)
             self.graph_a = self.graph_b = None       # the captured step reads the target buffer
 
+    def release_graphs(self):
+        """Drop every captured CUDA graph (they are re-captured on the next step).  Call before
+        ``torch.distributed.destroy_process_group()``: a graph that holds a captured NCCL all-reduce keeps the communicator
+        busy and tearing the process group down under it does not return."""
+        import gc
+        self.graph_a = self.graph_b = None
+        self._plans = {B: (pl, gt, None, None) for B, (pl, gt, _, _) in self._plans.items()}
+        gc.collect()
+        torch.cuda.synchronize(self.device)
+
     def set_lr(self, lr):
         """Change the learning rate (e.g. from a MultiStepLR schedule, train_mixer_h36m.py:65-67,249)."""
         if lr != self.lr:
