@@ -350,6 +350,34 @@ class TrainStep:
             self.gt = torch.empty(gt.shape, dtype=torch.float32, device=self.device)
             self.graph_a = self.graph_b = None       # the captured step reads the target buffer
 
+    # ---- optimiser state (the reference never saves it, train_mixer_h36m.py:276; resuming a run needs it) ----
+    def _named_flat(self):
+        names = {}
+        for n, p in self.model.named_parameters():
+            names.setdefault(id(p), n)
+        return [(names[id(p)], off, p.numel(), p.shape) for p, off in zip(self.flat.params, self.flat.offsets)]
+
+    def state_dict(self):
+        """Adam state keyed by parameter name (``exp_avg`` / ``exp_avg_sq`` like torch.optim.Adam) + step count and
+        hyper-parameters; pair it with ``model.state_dict()`` in a checkpoint."""
+        f = self.flat
+        return {"step": self.steps_done, "lr": self.lr, "weight_decay": self.wd, "betas": tuple(self.betas), "eps": self.eps,
+                "exp_avg": {n: f.m[o:o + k].view(sh).clone() for n, o, k, sh in self._named_flat()},
+                "exp_avg_sq": {n: f.v[o:o + k].view(sh).clone() for n, o, k, sh in self._named_flat()}}
+
+    def load_state_dict(self, sd):
+        f = self.flat
+        named = self._named_flat()
+        missing = [n for n, *_ in named if n not in sd["exp_avg"] or n not in sd["exp_avg_sq"]]
+        if missing:
+            raise KeyError("TrainStep.load_state_dict: missing optimiser state for %s" % missing)
+        with torch.no_grad():
+            for n, o, k, sh in named:
+                f.m[o:o + k].view(sh).copy_(sd["exp_avg"][n])
+                f.v[o:o + k].view(sh).copy_(sd["exp_avg_sq"][n])
+            self.step_dev.fill_(int(sd["step"]))
+        self.set_lr(float(sd.get("lr", self.lr)))
+
     def release_graphs(self):
         """Drop every captured CUDA graph (they are re-captured on the next step).  Call before
         ``torch.distributed.destroy_process_group()``: a graph that holds a captured NCCL all-reduce keeps the communicator
