@@ -104,8 +104,19 @@ static int launch_tc5(K kern, const A& a, int grid, int block, size_t smem, void
             if (slot >= 0) conf[slot] = Conf{(const void*)kern, dev, smem};
         }
     }
-    kern<<<grid, block, smem, (cudaStream_t)stream>>>(a);
-    cudaError_t e = cudaGetLastError();
+    // programmatic dependent launch: the kernel's parameter-only prologue may overlap the tail of the previous kernel in the
+    // stream (every kernel of this family calls griddepcontrol.wait before touching anything a predecessor writes)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = env_int("MMX_TC5_NO_PDL", 0) ? 0 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
     if (e != cudaSuccess) return fail(MMX_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
     return MMX_OK;
 }

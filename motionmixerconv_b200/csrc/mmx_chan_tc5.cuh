@@ -379,12 +379,13 @@ __global__ void __launch_bounds__(kThreadsChan) chan_fwd_kernel(const ChanArgs a
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc<TM_COLS>(cv.tslot);
-    __syncthreads();           // barriers initialised: the first tile can fly in while the weights are staged
+    pdl_launch_dependents();
     const int ntiles = (a.B + g.seq_per_tile - 1) / g.seq_per_tile;
     auto tile_nrows = [&](int tile) { return min(g.seq_per_tile, a.B - tile * g.seq_per_tile) * a.T; };
+    prologue<KP>(a, cv.w1b, cv.w2b, cv.c1f, cv.c2, cv.gam, cv.se1, cv.se2, tid);   // parameters only: overlaps the previous kernel's tail
+    pdl_wait();                // the previous kernel (the token half) has completed: x1 is readable
     if (warp == 0 && (int)blockIdx.x < ntiles)
         stage_in<VEC>(S, a.x1, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), a.H, g.pitch, &bars[0], lane);
-    prologue<KP>(a, cv.w1b, cv.w2b, cv.c1f, cv.c2, cv.gam, cv.se1, cv.se2, tid);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -567,14 +568,15 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc<TM_COLS>(cv.tslot);
-    __syncthreads();           // barriers initialised: the first tiles can fly in while the weights are staged
+    pdl_launch_dependents();
     const int ntiles = (a.B + g.seq_per_tile - 1) / g.seq_per_tile;
     auto tile_nrows = [&](int tile) { return min(g.seq_per_tile, a.B - tile * g.seq_per_tile) * a.T; };
+    prologue<KP>(a, cv.w1b, cv.w2b, cv.c1f, cv.c2, cv.gam, cv.se1, cv.se2, tid);   // parameters only: overlaps the previous kernel's tail
+    pdl_wait();                // the previous kernel has completed: x1 / dy are readable, the gradient buffers may be added to
     if (warp == 0 && (int)blockIdx.x < ntiles) {
         stage_in<VEC>(S1, a.x1, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), a.H, g.pitch, &bars[0], lane);
         stage_in<VEC>(S2, a.dy, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), a.H, g.pitch, &bars[2], lane);
     }
-    prologue<KP>(a, cv.w1b, cv.w2b, cv.c1f, cv.c2, cv.gam, cv.se1, cv.se2, tid);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();

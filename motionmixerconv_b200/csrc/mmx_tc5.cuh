@@ -173,6 +173,14 @@ MMX_TC5_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "m
 MMX_TC5_D void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 MMX_TC5_D void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------ programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still running: everything before pdl_wait() (barrier / TMEM set-up, staging of the weights -- nothing the predecessor
+// writes) overlaps the predecessor's tail; pdl_wait() returns once the predecessor has completed and its writes are visible.
+// pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as this kernel's CTAs have all started.
+MMX_TC5_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+MMX_TC5_D void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------ TF32 operand split
 // hi = x with the 13 low mantissa bits cleared (exactly what the tensor core keeps of an fp32 word), lo = x - hi (exact in
 // fp32; the tensor core again keeps its top bits).  hi*w_hi + lo*w_hi + hi*w_lo recovers the fp32 product to ~2^-21.

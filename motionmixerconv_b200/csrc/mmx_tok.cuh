@@ -217,8 +217,10 @@ __global__ void __launch_bounds__(kTokThreads) tok_fwd_kernel(const TokArgs a) {
     const Dropout dr = resolve_dropout(a.dr);
     const uint32_t key = chan::drop_key(dr.seed_lo, dr.seed_hi, a.site_base, dr.step);
     if (tid == 0) { mbar_init(&bars[0], 1); *abortf = 0; fence_mbar_init(); }
-    load_params(sm, m, a, tid);
+    pdl_launch_dependents();
+    load_params(sm, m, a, tid);        // parameters only: overlaps the previous kernel's tail
     __syncthreads();
+    pdl_wait();                        // the previous kernel has completed: x is readable
     const int ntiles = (a.B + S - 1) / S;
     const int s_l = tid / H, h = tid - s_l * H;
     const bool col_ok = tid < S * H;
@@ -328,7 +330,8 @@ __global__ void __launch_bounds__(kTokThreads, 2) tok_bwd_kernel(const TokArgs a
     const Dropout dr = resolve_dropout(a.dr);
     const uint32_t key = chan::drop_key(dr.seed_lo, dr.seed_hi, a.site_base, dr.step);
     if (tid == 0) { mbar_init(&bars[0], 1); *abortf = 0; fence_mbar_init(); }
-    load_params(sm, m, a, tid);
+    pdl_launch_dependents();
+    load_params(sm, m, a, tid);        // parameters only: overlaps the previous kernel's tail
     // staging area: rows [0,T] = N (row T: ones), [T+1, 2T] = DYT, [2T+1, 2T+tok] = DU, [2T+tok+1, 2T+2tok+1] = G (last: ones)
     const int CP = m.cols_pad;
     float* sN = sm + m.stg;
@@ -369,6 +372,7 @@ __global__ void __launch_bounds__(kTokThreads, 2) tok_bwd_kernel(const TokArgs a
 
     uint32_t ph = 0;
     auto tile_bytes = [&](int tile) { return (uint32_t)(min(S, a.B - tile * S) * T * H) * 4u; };
+    pdl_wait();                        // the previous kernel (the channel half backward) has completed: dx1 is readable
     const bool saved = a.x1s != nullptr && rr > 0;      // y recovered from the saved x1 (needed for the SE backward only)
     if (tid == 0 && (int)blockIdx.x < ntiles) {
         mbar_expect_tx(&bars[0], (saved ? 3 : 2) * tile_bytes(blockIdx.x));

