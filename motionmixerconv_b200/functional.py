@@ -113,10 +113,28 @@ def get_precision():
     return _PRECISION
 
 
+# Device-resident dropout step counter for the autograd path (None: the host-side step of the modules is all there is).  A
+# captured training step (rollout.RolloutTrainer) sets it and increments the tensor inside the graph, so every replay draws
+# fresh masks although the host-side step value is frozen into the captured launches.
+_STEP_DEV = None
+
+
+def set_dropout_step_tensor(t):
+    """t: int32 CUDA tensor with one element, or None."""
+    global _STEP_DEV
+    _STEP_DEV = t
+
+
+def _step_dev_ptr(step_dev):
+    if step_dev is not None:
+        return step_dev
+    return None if _STEP_DEV is None else _p(_STEP_DEV)
+
+
 def mlp_block_desc(B, T, H, tok, ch, se_hidden, act, use_se, use_max, training, block_index, p, seed, step, precision=None,
                    step_dev=None):
     return L.MmxMlpBlockDesc(B, T, H, tok, ch, se_hidden, L.MMX_ACT[act], int(use_se), int(use_max), int(training),
-                             block_index, L.MmxDropout(float(p), int(seed), int(step), step_dev),
+                             block_index, L.MmxDropout(float(p), int(seed), int(step), _step_dev_ptr(step_dev)),
                              L.MMX_PREC[precision or _PRECISION])
 
 
@@ -262,7 +280,7 @@ def conv_half_table(tensors, bn_aff=None):
 
 def conv_half_desc(B, C, T, E, kernel, pad, se_hidden, act, use_se, use_max, training, site, p, seed, step, step_dev=None):
     return L.MmxConvHalfDesc(B, C, T, E, kernel[0], kernel[1], pad[0], pad[1], se_hidden, L.MMX_ACT[act], int(use_se),
-                             int(use_max), int(training), site, L.MmxDropout(float(p), int(seed), int(step), step_dev))
+                             int(use_max), int(training), site, L.MmxDropout(float(p), int(seed), int(step), _step_dev_ptr(step_dev)))
 
 
 class _ConvHalf(torch.autograd.Function):

@@ -20,11 +20,18 @@ def _windows(args):
     return range(0, args.input_n_dataset + args.output_n_dataset - args.input_n_model - args.output_n_model + 1, args.step_window)
 
 
-def autoregressive_process_batch(batch, model, args, dim_used, teacher_forcing, check_nan=True):
-    """Same signature / return as the reference: ``(loss / n_windows, full_sequence_predict)``."""
+def autoregressive_process_batch(batch, model, args, dim_used, teacher_forcing, check_nan=False, loss_fn=None):
+    """Same signature / return as the reference: ``(loss / n_windows, full_sequence_predict)``.
+
+    ``check_nan=True`` restores the reference's ``assert not torch.isnan(loss)`` (``:256``), which costs a host
+    synchronisation per batch; the default leaves the check to the caller (``RolloutTrainer.nan_flag`` keeps it on the
+    device).  ``loss_fn``: override of the MPJPE loss (used by the CPU baseline, which runs this loop over the reference's
+    own modules)."""
     assert args.output_n_dataset % args.step_window == 0, "output_n_dataset does not divide by step_window"
     assert args.output_n_dataset // args.step_window >= 1, "output_n_dataset is smaller than step_window"
-    if args.loss_type == 'mpjpe':
+    if loss_fn is not None:
+        loss_fct = lambda pred, gt, out_n: loss_fn(pred, gt)
+    elif args.loss_type == 'mpjpe':
         loss_fct = lambda pred, gt, out_n: mpjpe_error(pred, gt)
     elif args.loss_type == 'angle':
         loss_fct = lambda pred, gt, out_n: torch.mean(
@@ -110,3 +117,82 @@ class RolloutExecutor:
             return self.out
         finally:
             self.model.train(was_training)
+
+
+class RolloutTrainer:
+    """One optimisation step of the autoregressive training loop (``train_autoregressive``, train_autoreg_mixer_h36m.py:110-135:
+    ``zero_grad; loss, _ = autoregressive_process_batch(...); loss.backward(); optimizer.step()``) as ONE CUDA-graph replay:
+    the chained forward passes, the window concatenations, the per-window losses, back-propagation through the predictions
+    (no teacher forcing) and the fused Adam update are captured once per batch shape.  The NaN check of the reference stays on
+    the device (``nan_flag``), so there is no host synchronisation in the loop.
+
+        tr = RolloutTrainer(model, args, dim_used, teacher_forcing=False, lr=1e-3)
+        loss, predict = tr.step(batch)          # static tensors, valid until the next step
+    """
+
+    def __init__(self, model, args, dim_used, teacher_forcing=False, lr=1e-3, weight_decay=1e-5, use_cuda_graph=True):
+        from .train import FusedAdam
+        self.model, self.args, self.teacher_forcing = model, args, teacher_forcing
+        self.dim_used = dim_used          # index tensor on the device is made at the first step (no host->device copy inside the capture)
+        self.opt = FusedAdam(model.parameters(), lr=lr, weight_decay=weight_decay)
+        self.use_graph = use_cuda_graph
+        self.graph = None
+        self.batch = None
+        self.loss = self.predict = self.nan_flag = None
+        self.step_dev = None
+
+    def _body(self):
+        from . import functional as F_
+        if self.step_dev is None:
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.batch.device)
+        F_.set_dropout_step_tensor(self.step_dev)      # dropout masks advance with a device-side counter (graph replays)
+        try:
+            loss, predict = autoregressive_process_batch(self.batch, self.model, self.args, self.dim_used, self.teacher_forcing, check_nan=False)
+            loss.backward()
+        finally:
+            F_.set_dropout_step_tensor(None)
+        self.opt.step()
+        self.step_dev.add_(len(_windows(self.args)))
+        return loss.detach().reshape(()), predict, torch.isnan(loss.detach()).reshape(())
+
+    def step(self, batch):
+        if not batch.is_cuda:
+            raise RuntimeError("RolloutTrainer needs CUDA tensors (the hot path has no CPU implementation)")
+        if not self.model.training:
+            raise RuntimeError("RolloutTrainer.step: the model is in eval() mode")
+        if not isinstance(self.dim_used, torch.Tensor) or self.dim_used.device != batch.device:
+            self.dim_used = torch.as_tensor(list(self.dim_used), dtype=torch.long).to(batch.device)
+        if not self.use_graph:
+            self.batch = batch
+            self.opt.zero_grad(set_to_none=True)
+            self.loss, self.predict, self.nan_flag = self._body()
+            return self.loss, self.predict
+        if self.graph is None or self.batch.shape != batch.shape:
+            self.batch = batch.clone()
+            side = torch.cuda.Stream(device=batch.device)
+            side.wait_stream(torch.cuda.current_stream())
+            # whole-step capture (fwd + bwd + optimiser): warm up on a side stream, restore the state the warm-up steps changed
+            state = [p.detach().clone() for p in self.model.parameters()] + [b.detach().clone() for b in self.model.buffers()]
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.opt.zero_grad(set_to_none=True)
+                    self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.no_grad():
+                for t, sv in zip(list(self.model.parameters()) + list(self.model.buffers()), state):
+                    t.copy_(sv)
+                for st in self.opt._flat.values():
+                    st["m"].zero_(); st["v"].zero_(); st["step"].zero_()
+                self.step_dev.zero_()
+            for m in self.model.modules():
+                if hasattr(m, "_calls"):
+                    m._calls = 0                      # dropout step counters of the blocks
+            self.opt.zero_grad(set_to_none=True)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss, self.predict, self.nan_flag = self._body()
+            # the capture itself did not execute anything: parameters / optimiser state are those before the first step
+        self.batch.copy_(batch)
+        self.graph.replay()
+        return self.loss, self.predict

@@ -120,3 +120,38 @@ def test_rollout_executor_cuda_graph_matches_eager():
         assert torch.equal(got, want)
         ref = _oracle_rollout_bptt(g.cfg, g.params, seq, np.float64)[1]
         check_close("predict", got.cpu().numpy(), ref.astype(np.float32), ref, rtol=1e-5)
+
+
+@pytest.mark.parametrize("teacher_forcing", [True, False])
+def test_rollout_trainer_cuda_graph_matches_eager_steps(teacher_forcing):
+    """RolloutTrainer (chained passes + BPTT + fused Adam as ONE graph replay, device-side NaN flag) against the eager loop
+    body of train_autoregressive (autoregressive_process_batch -> backward -> FusedAdam.step): same losses, same weights."""
+    from motionmixerconv_b200.rollout import RolloutTrainer, autoregressive_process_batch
+    from motionmixerconv_b200.train import FusedAdam
+    g = Golden("conv_k3_bn")
+    data = [torch.from_numpy(synthetic_full_windows(8, 35, 33, scale="ais", seed=s)).cuda() for s in (1, 2, 3)]
+    eager = _model(g.cfg, g.params).train()
+    opt = FusedAdam(eager.parameters(), lr=1e-3, weight_decay=1e-5)
+    want = []
+    for b in data:
+        opt.zero_grad(set_to_none=True)
+        loss, _ = autoregressive_process_batch(b, eager, ARGS, list(range(33)), teacher_forcing)
+        loss.backward()
+        opt.step()
+        want.append(float(loss.detach()))
+    model = _model(g.cfg, g.params).train()
+    tr = RolloutTrainer(model, ARGS, list(range(33)), teacher_forcing=teacher_forcing, lr=1e-3, weight_decay=1e-5)
+    got = []
+    for b in data:
+        loss, predict = tr.step(b)
+        got.append(float(loss))
+        assert predict.shape == (8, 25, 33) and not bool(tr.nan_flag)
+    np.testing.assert_allclose(got, want, rtol=2e-5)
+    bad = tot = 0
+    for (k, a), b_ in zip(eager.state_dict().items(), model.state_dict().values()):
+        if a.dtype.is_floating_point:
+            bad += int(((a - b_).abs() > 0.03 * 3e-3).sum())
+            tot += a.numel()
+        else:
+            assert torch.equal(a, b_), k                  # num_batches_tracked
+    assert bad / tot <= 0.01, (bad, tot)
