@@ -125,6 +125,12 @@ int mmx_linear_fwd(int rows, int K, int N, const float* x, const float* w, const
 /* dw,db accumulated; dx (may be null) written. */
 int mmx_linear_bwd(int rows, int K, int N, const float* x, const float* w, const float* dy, float* dw, float* db,
                    float* dx, void* stream);
+/* The same with a precision mode (MMX_PREC_*): MMX_PREC_TF32 runs the layer on the tensor cores (tcgen05, bf16 hi+lo split
+ * operands, fp32 accumulation; measured error ~1e-5 relative) when the shape is served (K+1, N <= 80, even; 16-byte aligned
+ * tensors), and falls back to the fp32 kernels otherwise.  The plain entry points above are precision MMX_PREC_FP32. */
+int mmx_linear_fwd_prec(int rows, int K, int N, const float* x, const float* w, const float* b, float* y, int precision, void* stream);
+int mmx_linear_bwd_prec(int rows, int K, int N, const float* x, const float* w, const float* dy, float* dw, float* db,
+                        float* dx, int precision, void* stream);
 
 typedef struct {
     float *ln_w, *ln_b;  /* LN.weight, LN.bias            [H]            */
@@ -137,6 +143,11 @@ typedef struct { int B, T, To, H, D; } MmxMlpHeadDesc;
 int mmx_mlp_head_fwd(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const float* x, float* out, void* stream);
 int mmx_mlp_head_bwd(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const MmxMlpHeadParams* grads,
                      const float* x, const float* dout, float* dx, void* stream);
+/* The same with a precision mode: MMX_PREC_TF32 runs the whole head as one tcgen05 kernel per direction (H < 64, D <= 80,
+ * T, To <= 128), see csrc/mmx_head_tc5.cuh; other shapes fall back to the fp32 kernels. */
+int mmx_mlp_head_fwd_prec(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const float* x, float* out, int precision, void* stream);
+int mmx_mlp_head_bwd_prec(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const MmxMlpHeadParams* grads,
+                          const float* x, const float* dout, float* dx, int precision, void* stream);
 
 /* ---------------- ConvMixer (h36m/conv_mixer_model.py, conv_mixer/encoding/positional_encoder.py) ---------------- */
 

@@ -89,6 +89,12 @@ SIGNATURES = {
     "mmx_linear_fwd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_linear_bwd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
+    "mmx_linear_fwd_prec": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "mmx_linear_bwd_prec": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_void_p]),
+    "mmx_mlp_head_fwd_prec": (C.c_int, [C.POINTER(MmxMlpHeadDesc), C.POINTER(MmxMlpHeadParams), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "mmx_mlp_head_bwd_prec": (C.c_int, [C.POINTER(MmxMlpHeadDesc), C.POINTER(MmxMlpHeadParams), C.POINTER(MmxMlpHeadParams),
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "mmx_mlp_head_fwd": (C.c_int, [C.POINTER(MmxMlpHeadDesc), C.POINTER(MmxMlpHeadParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_mlp_head_bwd": (C.c_int, [C.POINTER(MmxMlpHeadDesc), C.POINTER(MmxMlpHeadParams), C.POINTER(MmxMlpHeadParams),
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

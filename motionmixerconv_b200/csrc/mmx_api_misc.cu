@@ -88,6 +88,15 @@ int plan_head(const MmxMlpHeadDesc* d, bool bwd, MlpHeadDims* out, size_t* smem,
 }  // namespace mmx_tu_misc
 using namespace mmx_tu_misc;
 
+// tcgen05 kernels of the embedding / output head (mmx_api_io_tc5.cu)
+bool mmx_lin_tc5_ok(long long rows, int K, int N, const void* x, const void* y, const void* dx);
+int mmx_lin_tc5_fwd(long long rows, int K, int N, const float* x, const float* w, const float* b, float* y, void* stream);
+int mmx_lin_tc5_bwd(long long rows, int K, int N, const float* x, const float* w, const float* dy, float* dw, float* db, float* dx, void* stream);
+bool mmx_head_tc5_ok(const MmxMlpHeadDesc* d);
+int mmx_head_tc5_fwd(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const float* x, float* out, void* stream);
+int mmx_head_tc5_bwd(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const MmxMlpHeadParams* grads, const float* x, const float* dout,
+                     float* dx, void* stream);
+
 // ====================================================================================== C ABI
 extern "C" {
 
@@ -95,7 +104,15 @@ int mmx_version(void) { return 100; }
 const char* mmx_last_error(void) { return g_err.c_str(); }
 
 int mmx_linear_fwd(int rows, int K, int N, const float* x, const float* w, const float* b, float* y, void* stream) {
+    return mmx_linear_fwd_prec(rows, K, N, x, w, b, y, MMX_PREC_FP32, stream);
+}
+int mmx_linear_bwd(int rows, int K, int N, const float* x, const float* w, const float* dy, float* dw, float* db, float* dx, void* stream) {
+    return mmx_linear_bwd_prec(rows, K, N, x, w, dy, dw, db, dx, MMX_PREC_FP32, stream);
+}
+
+int mmx_linear_fwd_prec(int rows, int K, int N, const float* x, const float* w, const float* b, float* y, int precision, void* stream) {
     if (!x || !w || !b || !y) return fail(MMX_E_INVALID, "mmx_linear_fwd: null tensor");
+    if (precision == MMX_PREC_TF32 && mmx_lin_tc5_ok(rows, K, N, x, y, nullptr)) return mmx_lin_tc5_fwd(rows, K, N, x, w, b, y, stream);
     LinearFwdArgs a; size_t smem; int grid;
     int rc = plan_linear(rows, K, N, false, &a.d, &smem, &grid);
     if (rc) return rc;
@@ -103,9 +120,10 @@ int mmx_linear_fwd(int rows, int K, int N, const float* x, const float* w, const
     return launch<LinFwdBody>(a, grid, kThreads, smem, stream, 1);
 }
 
-int mmx_linear_bwd(int rows, int K, int N, const float* x, const float* w, const float* dy, float* dw, float* db,
-                   float* dx, void* stream) {
+int mmx_linear_bwd_prec(int rows, int K, int N, const float* x, const float* w, const float* dy, float* dw, float* db,
+                        float* dx, int precision, void* stream) {
     if (!x || !w || !dy || !dw || !db) return fail(MMX_E_INVALID, "mmx_linear_bwd: null tensor");
+    if (precision == MMX_PREC_TF32 && mmx_lin_tc5_ok(rows, K, N, x, dy, dx)) return mmx_lin_tc5_bwd(rows, K, N, x, w, dy, dw, db, dx, stream);
     LinearBwdArgs a; size_t smem; int grid;
     int rc = plan_linear(rows, K, N, true, &a.d, &smem, &grid);
     if (rc) return rc;
@@ -124,24 +142,35 @@ static int check_head_params(const MmxMlpHeadParams* p, const char* what) {
 }
 
 int mmx_mlp_head_fwd(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const float* x, float* out, void* stream) {
+    return mmx_mlp_head_fwd_prec(d, w, x, out, MMX_PREC_FP32, stream);
+}
+int mmx_mlp_head_bwd(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const MmxMlpHeadParams* grads,
+                     const float* x, const float* dout, float* dx, void* stream) {
+    return mmx_mlp_head_bwd_prec(d, w, grads, x, dout, dx, MMX_PREC_FP32, stream);
+}
+
+int mmx_mlp_head_fwd_prec(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const float* x, float* out, int precision, void* stream) {
     if (!x || !out) return fail(MMX_E_INVALID, "mmx_mlp_head_fwd: null tensor");
     MlpHeadFwdArgs a; size_t smem; int grid;
     int rc = plan_head(d, false, &a.d, &smem, &grid);
     if (rc) return rc;
     if ((rc = check_head_params(w, "mmx_mlp_head_fwd"))) return rc;
+    if (precision == MMX_PREC_TF32 && mmx_head_tc5_ok(d) && !((((uintptr_t)x) | ((uintptr_t)out)) & 15)) return mmx_head_tc5_fwd(d, w, x, out, stream);
     a.w = to_hw(w); a.x = x; a.out = out;
     if (d->T == 10) return launch<HeadFwdBody<10>>(a, grid, kThreads, smem, stream, 1);
     return launch<HeadFwdBody<0>>(a, grid, kThreads, smem, stream, 1);
 }
 
-int mmx_mlp_head_bwd(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const MmxMlpHeadParams* grads,
-                     const float* x, const float* dout, float* dx, void* stream) {
+int mmx_mlp_head_bwd_prec(const MmxMlpHeadDesc* d, const MmxMlpHeadParams* w, const MmxMlpHeadParams* grads,
+                          const float* x, const float* dout, float* dx, int precision, void* stream) {
     if (!x || !dout || !dx) return fail(MMX_E_INVALID, "mmx_mlp_head_bwd: null tensor");
     MlpHeadBwdArgs a; size_t smem; int grid;
     int rc = plan_head(d, true, &a.d, &smem, &grid);
     if (rc) return rc;
     if ((rc = check_head_params(w, "mmx_mlp_head_bwd"))) return rc;
     if ((rc = check_head_params(grads, "mmx_mlp_head_bwd(grads)"))) return rc;
+    if (precision == MMX_PREC_TF32 && mmx_head_tc5_ok(d) && !((((uintptr_t)x) | ((uintptr_t)dout) | ((uintptr_t)dx)) & 15))
+        return mmx_head_tc5_bwd(d, w, grads, x, dout, dx, stream);
     a.w = to_hw(w); a.g = to_hw(grads); a.x = x; a.dout = dout; a.dx = dx;
     const int tiles = ((d->D + 3) / 4) * ((d->H + 3) / 4);
     if (d->T == 10) {

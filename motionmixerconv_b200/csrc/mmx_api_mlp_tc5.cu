@@ -20,16 +20,15 @@ int mmx_mlp_tc5_bwd_saved(const MmxMlpBlockDesc*, const MmxMlpBlockParams*, cons
     return fail(MMX_E_UNSUPPORTED, "no tensor cores in the emulator");
 }
 #else
-#include <mutex>
-
 #include "mmx_chan_tc5.cuh"
+#include "mmx_tc5_launch.cuh"
 #include "mmx_tok.cuh"
 
 using namespace mmx;
 
 __device__ int g_mmx_tc5_abort = 0;
 
-static int* abort_ptr() {
+int* mmx_tc5_abort_ptr() {
     static int* p[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -45,7 +44,7 @@ static int* abort_ptr() {
 // number of kernels of this family whose pipeline waits timed out since the process started (0 in a healthy run); synchronises
 extern "C" int mmx_tc5_abort_count(void) {
     int v = 0;
-    cudaMemcpy(&v, abort_ptr(), sizeof(int), cudaMemcpyDeviceToHost);
+    cudaMemcpy(&v, mmx_tc5_abort_ptr(), sizeof(int), cudaMemcpyDeviceToHost);
     return v;
 }
 
@@ -83,44 +82,6 @@ bool mmx_mlp_tc5_ok(const MmxMlpBlockDesc* d) {
     return true;
 }
 
-template <class K, class A>
-static int launch_tc5(K kern, const A& a, int grid, int block, size_t smem, void* stream) {
-    struct Conf { const void* fn; int dev; size_t smem; };
-    static Conf conf[128];
-    static int nconf = 0;
-    static std::mutex mu;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        int slot = -1;
-        for (int i = 0; i < nconf; ++i)
-            if (conf[i].fn == (const void*)kern && conf[i].dev == dev) slot = i;
-        if (slot < 0 || conf[slot].smem < smem) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail(MMX_E_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-            if (slot < 0 && nconf < 128) slot = nconf++;
-            if (slot >= 0) conf[slot] = Conf{(const void*)kern, dev, smem};
-        }
-    }
-    // programmatic dependent launch: the kernel's parameter-only prologue may overlap the tail of the previous kernel in the
-    // stream (every kernel of this family calls griddepcontrol.wait before touching anything a predecessor writes)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(block);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = env_int("MMX_TC5_NO_PDL", 0) ? 0 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
-    if (e != cudaSuccess) return fail(MMX_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
-    return MMX_OK;
-}
-
 // ------------------------------------------------------------------------------------------ token half
 static int tok_S(const MmxMlpBlockDesc* d) {
     int S = imin(tok::kTokThreads / d->H, tok::kTokThreads / d->T);
@@ -141,7 +102,7 @@ static void fill_tok(tok::TokArgs& t, const MmxMlpBlockDesc* d, const MmxMlpBloc
     t.gate_out = nullptr; t.x1s = nullptr; t.gates = nullptr;
     t.S = S; t.site_base = d->block_index * 4;
     t.dr = make_dropout(d->dropout, d->training);
-    t.abort_count = abort_ptr();
+    t.abort_count = mmx_tc5_abort_ptr();
 }
 
 template <int ACT, int TT>
@@ -178,7 +139,7 @@ static void fill_chan(chan::ChanArgs& c, const MmxMlpBlockDesc* d, const MmxMlpB
     c.B = d->B; c.T = d->T; c.H = d->H; c.ch = d->ch; c.rr = d->use_se ? d->se_hidden : 0;
     c.site_base = d->block_index * 4;
     c.dr = make_dropout(d->dropout, d->training);
-    c.abort_count = abort_ptr();
+    c.abort_count = mmx_tc5_abort_ptr();
 }
 
 template <int ACT, int KP, int VEC>

@@ -655,13 +655,14 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
             gemm3<0, 0>(tU, xB, xB + P::PLANE, P::PS, w1B, w1B + P::WPLANE, P::WPS, KP, KP / 16, false);
             mma_commit(&bars[1]);
         }
-        // ---------------- E1: G2 = reg1(act(U2 + b1')) -> operand Y (ones column at ch); U2 stays in TMEM
+        // ---------------- E1: G2 = reg1(act(U2 + b1')) -> operand Y (ones column at ch); TMEM keeps reg1'(.) * act'(U2 + b1')
+        // in place of U2 (what the backward needs of it), so the activation is evaluated once per element and tile
         mbar_wait(&bars[1], ph_mma, abortf);
         ph_mma ^= 1;
         tc_fence_after();
 #pragma unroll 1
         for (int c8 = half; c8 < NCH; c8 += kHalves) {
-            float u[8], b[8];
+            float u[8], b[8], dact[8];
             tmem_ld8(tmem_addr(tU, qtr, 8 * c8), u);
             ld8s(cv.c1f + 8 * c8, b);
             const uint32_t kb = th16 ? keep8(key2, th16, grow, ch8, c8) : 0xffu;
@@ -669,12 +670,16 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = 8 * c8 + j;
-                float gv = act_fwd<ACT>(u[j] + b[j]);
-                gv = (kb >> j) & 1u ? gv * dr.scale : 0.0f;
-                u[j] = !valid ? 0.0f : (c < ch ? gv : (c == ch ? 1.0f : 0.0f));
+                float gv;
+                const float da = act_fwd_grad<ACT>(u[j] + b[j], &gv);
+                const float ks = (kb >> j) & 1u ? dr.scale : 0.0f;
+                dact[j] = (valid && c < ch) ? da * ks : 0.0f;
+                u[j] = !valid ? 0.0f : (c < ch ? gv * ks : (c == ch ? 1.0f : 0.0f));
             }
             put_chunk(bufY, P::PLANE, P::PS, prow, c8, u);
+            tmem_st8(tmem_addr(tU, qtr, 8 * c8), dact);
         }
+        tmem_wait_st();
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -766,27 +771,19 @@ __global__ void __launch_bounds__(kThreadsChan) chan_bwd_kernel(const ChanArgs a
             gemm3<1, 1>(tDW2, xB, xB + P::PLANE, P::PS, yB, yB + P::PLANE, P::PS, KP, 128 / 16, !first);
             mma_commit(&bars[1]);
         }
-        // ---------------- E3: dU2 = reg1'(dG2) * act'(U2 + b1') -> operand Y; xhat -> operand X again
+        // ---------------- E3: dU2 = dG2 * (reg1' act')(stored in TMEM by E1) -> operand Y; xhat -> operand X again
         mbar_wait(&bars[1], ph_mma, abortf);
         ph_mma ^= 1;
         tc_fence_after();
 #pragma unroll 1
         for (int c8 = half; c8 < NCH; c8 += kHalves) {
-            float u[8], dg[8], xh[8], b[8];
-            tmem_ld8(tmem_addr(tU, qtr, 8 * c8), u);
+            float u[8], dg[8], xh[8];
+            tmem_ld8(tmem_addr(tU, qtr, 8 * c8), u);          // reg1' * act' (stored by E1)
             tmem_ld8(tmem_addr(tY, qtr, 8 * c8), dg);
             tmem_ld8(tmem_addr(tXH, qtr, 8 * c8), xh);
-            ld8s(cv.c1f + 8 * c8, b);
-            const uint32_t kb = th16 ? keep8(key2, th16, grow, ch8, c8) : 0xffu;
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float av;
-                const float dact = act_fwd_grad<ACT>(u[j] + b[j], &av);
-                float d = dg[j] * dact;
-                d = (kb >> j) & 1u ? d * dr.scale : 0.0f;
-                u[j] = (valid && 8 * c8 + j < ch) ? d : 0.0f;
-            }
+            for (int j = 0; j < 8; ++j) u[j] *= dg[j];
             put_chunk(bufY, P::PLANE, P::PS, prow, c8, u);
             put_chunk(bufX, P::PLANE, P::PS, prow, c8, xh);
         }

@@ -54,13 +54,14 @@ def _call(name, *args):
 # ------------------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, precision):
         x, w, b = _chk(x, "x"), _chk(w, "weight"), _chk(b, "bias")
+        ctx.prec = L.MMX_PREC[precision or _PRECISION]
         K, N = x.shape[-1], b.numel()
         rows = x.numel() // K
         y = torch.empty(*x.shape[:-1], N, dtype=torch.float32, device=x.device)
         with torch.cuda.device_of(x):
-            _call("mmx_linear_fwd", rows, K, N, _p(x), _p(w), _p(b), _p(y), _stream())
+            _call("mmx_linear_fwd_prec", rows, K, N, _p(x), _p(w), _p(b), _p(y), ctx.prec, _stream())
         ctx.save_for_backward(x, w)
         ctx.need_dx = ctx.needs_input_grad[0]      # not x.requires_grad: _chk may have returned a contiguous copy made under no_grad
         ctx.wshape = w.shape
@@ -75,12 +76,13 @@ class _Linear(torch.autograd.Function):
         dw, db = _zeros_like_many([w, dy.new_empty(N)])
         dx = torch.empty_like(x) if ctx.need_dx else None
         with torch.cuda.device_of(x):
-            _call("mmx_linear_bwd", rows, K, N, _p(x), _p(w), _p(dy), _p(dw), _p(db), _p(dx), _stream())
-        return dx, dw.view(ctx.wshape), db
+            _call("mmx_linear_bwd_prec", rows, K, N, _p(x), _p(w), _p(dy), _p(dw), _p(db), _p(dx), ctx.prec, _stream())
+        return dx, dw.view(ctx.wshape), db, None
 
 
-def linear(x, weight, bias):
-    return _Linear.apply(x, weight, bias)
+def linear(x, weight, bias, precision=None):
+    """precision: None (follow ``set_precision``) | "fp32" | "tf32" (tensor cores, see mmx_linear_fwd_prec)."""
+    return _Linear.apply(x, weight, bias, precision)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -206,15 +208,16 @@ def mlp_head_table(tensors):
 
 class _MlpHead(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, wt, bt, wf, bf):
+    def forward(ctx, x, ln_w, ln_b, wt, bt, wf, bf, precision):
         x = _chk(x, "x")
+        ctx.prec = L.MMX_PREC[precision or _PRECISION]
         params = [_chk(q, "parameter") for q in (ln_w, ln_b, wt, bt, wf, bf)]
         B, T, H = x.shape
         To, D = bt.numel(), bf.numel()
         desc = L.MmxMlpHeadDesc(B, T, To, H, D)
         out = torch.empty(B, To, D, dtype=torch.float32, device=x.device)
         with torch.cuda.device_of(x):
-            _call("mmx_mlp_head_fwd", C.byref(desc), C.byref(mlp_head_table(params)), _p(x), _p(out), _stream())
+            _call("mmx_mlp_head_fwd_prec", C.byref(desc), C.byref(mlp_head_table(params)), _p(x), _p(out), ctx.prec, _stream())
         ctx.save_for_backward(x, *params)
         return out
 
@@ -228,13 +231,13 @@ class _MlpHead(torch.autograd.Function):
         grads = _zeros_like_many(params)
         dx = torch.empty_like(x)
         with torch.cuda.device_of(x):
-            _call("mmx_mlp_head_bwd", C.byref(desc), C.byref(mlp_head_table(params)), C.byref(mlp_head_table(grads)),
-                  _p(x), _p(dout), _p(dx), _stream())
-        return (dx, *grads)
+            _call("mmx_mlp_head_bwd_prec", C.byref(desc), C.byref(mlp_head_table(params)), C.byref(mlp_head_table(grads)),
+                  _p(x), _p(dout), _p(dx), ctx.prec, _stream())
+        return (dx, *grads, None)
 
 
-def mlp_head(x, ln_w, ln_b, wt, bt, wf, bf):
-    return _MlpHead.apply(x, ln_w, ln_b, wt, bt, wf, bf)
+def mlp_head(x, ln_w, ln_b, wt, bt, wf, bf, precision=None):
+    return _MlpHead.apply(x, ln_w, ln_b, wt, bt, wf, bf, precision)
 
 
 # ------------------------------------------------------------------------------------------------

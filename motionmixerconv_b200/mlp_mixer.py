@@ -143,12 +143,14 @@ class MlpMixer(nn.Module):
         self.fc_out = nn.Linear(self.hidden_dim, self.num_classes)
         self.pred_len = pred_len
         self.conv_out = nn.Conv1d(self.seq_len, self.pred_len, 1, stride=1)
+        self.precision = None         # None: functional.get_precision(); set through set_precision()
 
     def set_precision(self, precision):
         """"fp32" (1e-5 parity, default) | "tf32" (tensor-core contractions inside the MixerBlocks, 2e-3 parity) | None
         (follow ``functional.set_precision``).  Not a reference argument: the constructor signature stays the reference's."""
         if precision is not None and precision not in F_.L.MMX_PREC:
             raise ValueError("unknown precision %r" % (precision,))
+        self.precision = precision
         for mb in self.Mixer_Block:
             mb.precision = precision
         return self
@@ -157,8 +159,8 @@ class MlpMixer(nn.Module):
         """x: [B, seq_len, input_size] -> [B, pred_len, num_classes]  (mlp_mixer.py:306-337)."""
         if x.dim() != 3 or x.shape[1] != self.seq_len or x.shape[2] != self.input_size:
             raise RuntimeError("MlpMixer.forward: expected [B, %d, %d], got %s" % (self.seq_len, self.input_size, tuple(x.shape)))
-        y = F_.linear(x, self.conv.weight, self.conv.bias)       # Conv2d(1,H,(1,D)) == per-frame Linear
+        y = F_.linear(x, self.conv.weight, self.conv.bias, self.precision)       # Conv2d(1,H,(1,D)) == per-frame Linear
         for mb in self.Mixer_Block:
             y = mb(y)
         return F_.mlp_head(y, self.LN.weight, self.LN.bias, self.conv_out.weight, self.conv_out.bias,
-                           self.fc_out.weight, self.fc_out.bias)
+                           self.fc_out.weight, self.fc_out.bias, self.precision)

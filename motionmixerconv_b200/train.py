@@ -113,7 +113,8 @@ class _MlpMixerPlan:
     def forward(self, lib, st, training):
         md = self.model
         T, H, D = md.seq_len, md.hidden_dim, md.input_size
-        L.check(lib, lib.mmx_linear_fwd(self.B * T, D, H, _p(self.x), _p(self.conv_w), _p(self.conv_b), _p(self.acts[0]), st), "mmx_linear_fwd")
+        prec = L.MMX_PREC[md.precision or F_.get_precision()]
+        L.check(lib, lib.mmx_linear_fwd_prec(self.B * T, D, H, _p(self.x), _p(self.conv_w), _p(self.conv_b), _p(self.acts[0]), prec, st), "mmx_linear_fwd")
         for i, (mb, tw, _) in enumerate(self.blocks):
             d = self._desc(mb, training)
             if training and self.saves[i]:
@@ -121,15 +122,16 @@ class _MlpMixerPlan:
                                                         _p(self.gate[i]), st), "mmx_mlp_block_fwd_save")
             else:
                 L.check(lib, lib.mmx_mlp_block_fwd(C.byref(d), C.byref(tw), _p(self.acts[i]), _p(self.acts[i + 1]), st), "mmx_mlp_block_fwd")
-        L.check(lib, lib.mmx_mlp_head_fwd(C.byref(self.head_desc), C.byref(self.head_w), _p(self.acts[-1]), _p(self.pred), st), "mmx_mlp_head_fwd")
+        L.check(lib, lib.mmx_mlp_head_fwd_prec(C.byref(self.head_desc), C.byref(self.head_w), _p(self.acts[-1]), _p(self.pred), prec, st), "mmx_mlp_head_fwd")
         return self.pred
 
     def backward(self, lib, st):
         md = self.model
         T, H, D = md.seq_len, md.hidden_dim, md.input_size
         cur = self.dact[0]
-        L.check(lib, lib.mmx_mlp_head_bwd(C.byref(self.head_desc), C.byref(self.head_w), C.byref(self.head_g),
-                                          _p(self.acts[-1]), _p(self.dpred), _p(cur), st), "mmx_mlp_head_bwd")
+        prec = L.MMX_PREC[md.precision or F_.get_precision()]
+        L.check(lib, lib.mmx_mlp_head_bwd_prec(C.byref(self.head_desc), C.byref(self.head_w), C.byref(self.head_g),
+                                               _p(self.acts[-1]), _p(self.dpred), _p(cur), prec, st), "mmx_mlp_head_bwd")
         for i in reversed(range(len(self.blocks))):
             mb, tw, tg = self.blocks[i]
             nxt = self.dact[1] if cur is self.dact[0] else self.dact[0]
@@ -140,7 +142,7 @@ class _MlpMixerPlan:
             else:
                 L.check(lib, lib.mmx_mlp_block_bwd(C.byref(d), C.byref(tw), C.byref(tg), _p(self.acts[i]), _p(cur), _p(nxt), st), "mmx_mlp_block_bwd")
             cur = nxt
-        L.check(lib, lib.mmx_linear_bwd(self.B * T, D, H, _p(self.x), _p(self.conv_w), _p(cur), _p(self.conv_gw), _p(self.conv_gb), None, st), "mmx_linear_bwd")
+        L.check(lib, lib.mmx_linear_bwd_prec(self.B * T, D, H, _p(self.x), _p(self.conv_w), _p(cur), _p(self.conv_gw), _p(self.conv_gb), None, prec, st), "mmx_linear_bwd")
 
 
 class _ConvMixerPlan:
