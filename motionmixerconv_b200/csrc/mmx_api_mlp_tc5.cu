@@ -66,9 +66,16 @@ extern "C" int mmx_tc5_dropout_mask(const MmxDropout* d, unsigned int site, long
     return MMX_OK;
 }
 
+// defined in mmx_api_mlp_wide.cu: the wide variant of the channel half (80 <= max(H, ch) <= 128, weights streamed from a workspace)
+int mmx_chan_wide_run(bool bwd, int act, const void* chan_args, void* stream);
+
+// padded operand width: 64 / 80 (resident weights, bias gradients in a ones column) or 128 (the wide variant); 0: not served
 static int kp_of(const MmxMlpBlockDesc* d) {
     const int need = (d->H > d->ch ? d->H : d->ch) + 1;      // + the ones column that carries the bias gradients
-    return need <= 64 ? 64 : (need <= 80 ? 80 : 0);
+    if (need <= 64) return 64;
+    if (need <= 80) return 80;
+    if (need - 1 <= 128 && !(d->ch & 1) && !env_int("MMX_MLP_NO_WIDE", 0)) return 128;
+    return 0;
 }
 
 bool mmx_mlp_tc5_ok(const MmxMlpBlockDesc* d) {
@@ -166,6 +173,7 @@ static int chan_dispatch_act(bool bwd, const MmxMlpBlockDesc* d, const chan::Cha
     return vec4 ? run_chan<ACT, 80, 4>(bwd, c, stream) : run_chan<ACT, 80, 2>(bwd, c, stream);
 }
 static int chan_dispatch(bool bwd, const MmxMlpBlockDesc* d, const chan::ChanArgs& c, void* stream) {
+    if (kp_of(d) == 128) return mmx_chan_wide_run(bwd, d->act, &c, stream);
     return d->act == MMX_ACT_GELU ? chan_dispatch_act<ACT_GELU>(bwd, d, c, stream) : chan_dispatch_act<ACT_MISH>(bwd, d, c, stream);
 }
 

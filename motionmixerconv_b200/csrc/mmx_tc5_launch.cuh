@@ -9,8 +9,8 @@ int* mmx_tc5_abort_ptr();
 
 namespace mmx {
 
-template <class K, class A>
-static int launch_tc5(K kern, const A& a, int grid, int block, size_t smem, void* stream) {
+template <class K, class... A>
+static int launch_tc5v(K kern, int grid, int block, size_t smem, void* stream, const A&... a) {
     struct Conf { const void* fn; int dev; size_t smem; };
     static Conf conf[128];
     static int nconf = 0;
@@ -42,10 +42,13 @@ static int launch_tc5(K kern, const A& a, int grid, int block, size_t smem, void
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = env_int("MMX_TC5_NO_PDL", 0) ? 0 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a...);
     if (e != cudaSuccess) return fail(MMX_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
     return MMX_OK;
 }
-
+template <class K, class A>
+static int launch_tc5(K kern, const A& a, int grid, int block, size_t smem, void* stream) {
+    return launch_tc5v(kern, grid, block, smem, stream, a);
+}
 
 }  // namespace mmx

@@ -213,14 +213,132 @@ def test_dropout_forward_and_backward_vs_oracle_with_the_same_masks(B):
 
 
 def test_unsupported_shapes_fall_back_to_fp32_kernels():
-    """tf32 is a permission: H = 128 (K4) is not served by the tcgen05 family yet and must give the FP32 result."""
+    """tf32 is a permission: H = 256 is not served by the tcgen05 family and must give the FP32 result."""
+    cfg = dict(Golden("mlp_k2").cfg, num_blocks=1, hidden_dim=256, channels_mlp_dim=64)
+    m = _model(cfg, None, seed=1).eval()
+    x = torch.from_numpy(synthetic_pose_windows(9, 10, 10, 66, scale="amass", seed=2)[0]).cuda()
+    with torch.no_grad():
+        a = m(x)
+        b = m.set_precision("fp32")(x)
+    assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------ wide variant (80 <= max(H, ch) <= 128)
+def test_wide_family_serves_k4():
+    """K4 (AMASS-shaped, H = ch = 128): the wide tcgen05 channel half (csrc/mmx_chan_wide.cuh) is what runs."""
+    from motionmixerconv_b200 import _lib as L
+    from motionmixerconv_b200 import functional as F_
+    for H, ch, want in [(128, 128, 1), (96, 128, 1), (128, 80, 1), (130, 64, 0), (64, 130, 0), (128, 127, 0)]:
+        desc = F_.mlp_block_desc(64, 10, H, 20, ch, 1, "gelu", True, False, True, 0, 0.0, 0, 0, "tf32")
+        assert L.load().mmx_mlp_block_saves(C.byref(desc)) == want, (H, ch)
     g = Golden("mlp_k4")
     m = _model(g.cfg, g.params).eval()
     x = torch.from_numpy(g.x).cuda()
     with torch.no_grad():
         a = m(x)
         b = m.set_precision("fp32")(x)
-    assert torch.equal(a, b)
+    d = (a - b).abs().max().item() / b.abs().max().item()
+    assert 0.0 < d < TOL, d
+    _assert_healthy()
+
+
+def test_golden_k4():
+    g = Golden("mlp_k4")
+    model = _model(dict(g.cfg), g.params).train()
+    pred, loss, grads, dx = _run(model, g.x, g.gt)
+    check_close("pred vs reference", pred, g.pred, rtol=TOL)
+    assert abs(loss - g.loss) <= TOL * abs(g.loss)
+    floor = 0.01 * TOL * grad_scale(g.grads)
+    for k, want in g.grads.items():
+        check_close("grad " + k, grads[k], want, rtol=TOL, atol=floor)
+    check_close("dx", dx, g.dx, rtol=TOL)
+    model.eval()
+    with torch.no_grad():
+        pe = model(torch.from_numpy(g.x).cuda()).cpu().numpy()
+    check_close("pred_eval", pe, g.pred_eval, rtol=TOL)
+    _assert_healthy()
+
+
+@pytest.mark.parametrize("B", [1, 12, 13, 333, 2000, 4096])
+def test_wide_ragged_batches_vs_oracle(B):
+    """K4 at batch sizes around the 12-sequence MMA tile, and the benchmark size (342 tiles on 148 CTAs: the weight slot
+    cycles W1' -> W2 -> W1' several times per CTA, dW accumulates in TMEM across tiles)."""
+    g = Golden("mlp_k4")
+    c = dict(g.cfg, regularization=0)
+    x, gt = synthetic_pose_windows(B, c["seq_len"], c["pred_len"], c["input_size"], scale="amass", seed=7)
+    model = _model(c, g.params).train()
+    _compare(*_run(model, x, gt), _oracle(c, g.params, x, gt))
+    _assert_healthy()
+
+
+WIDE_VARIANTS = {
+    "h96_ch128_mish": dict(hidden_dim=96, channels_mlp_dim=128, activation="mish"),
+    "h128_ch100": dict(hidden_dim=128, channels_mlp_dim=100),
+    "h100_ch84_no_se": dict(hidden_dim=100, channels_mlp_dim=84, use_se=False),
+    "h90_ch128": dict(hidden_dim=90, channels_mlp_dim=128, activation="mish"),          # H % 4 != 0: 8-byte row accesses
+    "h80_ch80": dict(hidden_dim=80, channels_mlp_dim=80),                              # the first width the 80-column plan cannot hold
+    "h128_T16": dict(hidden_dim=128, channels_mlp_dim=128, seq_len=16, pred_len=25, tokens_mlp_dim=32, r_se=8),
+}
+
+
+@pytest.mark.parametrize("name", sorted(WIDE_VARIANTS))
+def test_wide_shape_variants_vs_oracle(name):
+    cfg = dict(Golden("mlp_k4").cfg, num_blocks=2, regularization=0, **WIDE_VARIANTS[name])
+    model = _model(cfg, None, seed=3).train()
+    params = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    x, gt = synthetic_pose_windows(301, cfg["seq_len"], cfg["pred_len"], cfg["input_size"], scale="amass", seed=9)
+    _compare(*_run(model, x, gt), _oracle(cfg, params, x, gt))
+    _assert_healthy()
+
+
+def test_wide_dropout_vs_oracle_with_the_same_masks():
+    g = Golden("mlp_k4")
+    c = dict(g.cfg, regularization=0.1)
+    x, gt = synthetic_pose_windows(77, c["seq_len"], c["pred_len"], c["input_size"], scale="amass", seed=21)
+    torch.manual_seed(4321)
+    model = _model(c, g.params, seed=4321).train()
+    masks = MK.mlp_tc5_masks(c, len(x), 4321, step=0)
+    _compare(*_run(model, x, gt), _oracle(c, g.params, x, gt, masks=masks))
+    _assert_healthy()
+
+
+def test_wide_save_variant_and_in_place_recompute_variant_agree():
+    from motionmixerconv_b200 import _lib as L
+    from motionmixerconv_b200 import functional as F_
+    torch.manual_seed(0)
+    B, T, H, tok, ch = 500, 10, 128, 20, 128
+    lib = L.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    shapes = [(H,), (H,), (tok, T), (tok,), (T, tok), (T,), (H,), (H,), (ch, H), (ch,), (H, ch), (H,), (1, T), (T, 1)]
+    params = [torch.randn(*s, device="cuda") * 0.2 for s in shapes]
+    params[0] += 1.0
+    params[6] += 1.0
+    x, dy = torch.randn(B, T, H, device="cuda"), torch.randn(B, T, H, device="cuda")
+    desc = F_.mlp_block_desc(B, T, H, tok, ch, 1, "gelu", True, False, True, 1, 0.1, 1234, 5, "tf32")
+    tw = F_.mlp_block_table(params)
+
+    def run(saved):
+        y, dx = torch.empty_like(x), torch.empty_like(x)
+        grads = [torch.zeros_like(p) for p in params]
+        tg = F_.mlp_block_table(grads)
+        if saved:
+            x1, gate = torch.empty_like(x), torch.empty(B, T, device="cuda")
+            L.check(lib, lib.mmx_mlp_block_fwd_save(C.byref(desc), C.byref(tw), x.data_ptr(), y.data_ptr(), x1.data_ptr(), gate.data_ptr(), st), "fwd")
+            L.check(lib, lib.mmx_mlp_block_bwd_saved(C.byref(desc), C.byref(tw), C.byref(tg), x.data_ptr(), x1.data_ptr(), gate.data_ptr(),
+                                                     dy.data_ptr(), dx.data_ptr(), st), "bwd")
+        else:
+            L.check(lib, lib.mmx_mlp_block_fwd(C.byref(desc), C.byref(tw), x.data_ptr(), y.data_ptr(), st), "fwd")
+            L.check(lib, lib.mmx_mlp_block_bwd(C.byref(desc), C.byref(tw), C.byref(tg), x.data_ptr(), dy.data_ptr(), dx.data_ptr(), st), "bwd")
+        torch.cuda.synchronize()
+        return y, dx, grads
+
+    ya, dxa, ga = run(False)
+    yb, dxb, gb = run(True)
+    assert torch.equal(ya, yb)
+    assert (dxa - dxb).abs().max().item() <= 1e-4 * dxa.abs().max().item()
+    for a, b in zip(ga, gb):
+        assert (a - b).abs().max().item() <= 1e-4 * max(a.abs().max().item(), 1e-6)
+    _assert_healthy()
 
 
 def test_mpjpe_after_200_steps_within_0p1mm_of_oracle():

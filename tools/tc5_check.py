@@ -104,6 +104,14 @@ def main():
         print(json.dumps(block_timing(4096, 64, 64, "gelu", "tf32", 0.1)), flush=True)
         print(json.dumps(block_timing(4096, 64, 64, "gelu", "fp32", 0.1)), flush=True)
         print("abort_count", lib.mmx_tc5_abort_count(), flush=True)
+    if "timing_wide" in what:
+        for B in (4096, 16384):
+            for prec in ("tf32", "fp32"):
+                if prec == "fp32" and B > 4096:
+                    continue
+                print(json.dumps(block_timing(B, 128, 128, "gelu", prec, 0.1)), flush=True)
+        print(json.dumps(block_timing(4096, 96, 96, "mish", "tf32", 0.1)), flush=True)
+        print("abort_count", lib.mmx_tc5_abort_count(), flush=True)
 
 
 if __name__ == "__main__":
