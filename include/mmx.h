@@ -109,6 +109,41 @@ int mmx_mlp_channel_half_fwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* 
 int mmx_mlp_channel_half_bwd(const MmxMlpBlockDesc* d, const MmxMlpBlockParams* w, const MmxMlpBlockParams* grads, const float* x1,
                              const float* dy, float* dx1, void* stream);
 
+/* ---- MixerBlock with regularization == -1: BatchNorm1d inside the MLP blocks (mlp_mixer.py:72-73 reg1 / reg2, applied at :90-94) ----
+ * Batch statistics are global over the batch, so the block runs as a chain of stage kernels sequenced by the caller
+ * (motionmixerconv_b200/functional.py MlpBnBlock); the fc layers are mmx_linear_{fwd,bwd}:
+ *   token half  : ln_fwd (Tt = T: output transposed [B,H,T]) -> fc1 -> bn1d_stats/finalize/apply (act) -> fc2 -> bn1d_stats/finalize
+ *                 -> se_res_fwd (v transposed, affine per h)                              BatchNorm1d(hidden_dim): [N,C,L] = [B,H,*]
+ *   channel half: ln_fwd -> fc1 -> bn1d_stats/finalize/apply (act) -> fc2 -> bn1d_stats/finalize -> se_res_fwd (affine per t)
+ *                                                                                          BatchNorm1d(seq_len):    [N,C,L] = [B,T,*]
+ * and the backward mirrors it: se_res_bwd -> bn1d_bwd_reduce / mmx_bn_coef / bn1d_bwd_apply -> fc2 bwd -> ... -> ln_bwd.
+ * Per-channel vectors as in the ConvMixer BatchNorm path: bn = [scale|shift|xs|xo][C] (mmx_bn_finalize), coef = [k1|k2|k3][C]
+ * (mmx_bn_coef).  act: MMX_ACT_* (the statistic is taken AFTER the activation, u is the pre-activation) or -1 (identity). */
+/* y = LayerNorm(x) over rows of width H (eps 1e-5); stats[r] = (mean, rstd).  Tt > 0: row r = (b, t) of [B,Tt,H] and y is
+ * written transposed, y[b][h][t]  (mlp_mixer.py:146-149). */
+int mmx_ln_fwd(long long rows, int H, int Tt, const float* x, const float* g, const float* b, float* y, float* stats, void* stream);
+/* dx = res (nullable) + LayerNorm backward of dy (Tt > 0: dy laid out [B][H][Tt]); dg, db accumulated.  dx may alias res. */
+int mmx_ln_bwd(long long rows, int H, int Tt, const float* x, const float* stats, const float* g, const float* dy, const float* res,
+               float* dx, float* dg, float* db, void* stream);
+/* u: [N,C,L].  sums[0:C] += sum_{n,l} a, sums[C:2C] += sum a^2, a = act(u)  (then mmx_bn_finalize with n = N*L). */
+int mmx_bn1d_stats(long long N, int C, int L, int act, const float* u, double* sums, void* stream);
+/* y = act(u) * scale[c] + shift[c]  (bn[0:C], bn[C:2C]; eval mode: the running-statistics affine). */
+int mmx_bn1d_apply(long long N, int C, int L, int act, const float* u, const float* bn, float* y, void* stream);
+/* sums[0:C] += sum dy, sums[C:2C] += sum dy * xhat, xhat = act(u)*xs[c] + xo[c]  (then mmx_bn_coef). */
+int mmx_bn1d_bwd_reduce(long long N, int C, int L, int act, const float* u, const float* bn, const float* dy, double* sums, void* stream);
+/* du = k1[c] * (dy - k2[c] - xhat*k3[c]) * act'(u); du may alias dy. */
+int mmx_bn1d_bwd_apply(long long N, int C, int L, int act, const float* u, const float* bn, const float* coef, const float* dy,
+                       float* du, void* stream);
+/* out = x + SE(y), y = v*scale + shift (the second BatchNorm of the MlpBlock folded in; mlp_mixer.py:152-155, 161-164, SELayer
+ * :30-34).  x, out: [B,T,H]; v: [B,T,H] or, v_transposed, [B,H,T]; the affine is indexed by h (affine_by_h, token half) or by t.
+ * se_hidden == 0: no SE (gate 1). */
+int mmx_se_res_fwd(int B, int T, int H, int se_hidden, int use_max_pooling, int v_transposed, int affine_by_h, const float* x,
+                   const float* v, const float* bn, const float* se_w1, const float* se_w2, float* out, void* stream);
+/* dv (v's layout) = gradient wrt y of the same; SE weight gradients accumulated.  (The residual's gradient is dout itself.) */
+int mmx_se_res_bwd(int B, int T, int H, int se_hidden, int use_max_pooling, int v_transposed, int affine_by_h, const float* v,
+                   const float* bn, const float* se_w1, const float* se_w2, const float* dout, float* g_se_w1, float* g_se_w2,
+                   float* dv, void* stream);
+
 /* Diagnostics of the tcgen05 / TMEM MixerBlock kernels (precision == MMX_PREC_TF32): number of kernels whose mbarrier waits
  * timed out since the process started (a mis-programmed pipeline ends the kernel instead of hanging the GPU); 0 in a healthy
  * run.  Synchronises the device. */
@@ -203,7 +238,7 @@ int mmx_conv_half_bn_bwd2(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, 
 /* BatchNorm bookkeeping between the passes (nn.BatchNorm2d semantics; C elements, one tiny launch each instead of ~25 tensor ops):
  * bn_finalize: sums -> bn = [scale|shift|xs|xo]; running_mean/var updated (momentum, unbiased variance), num_batches_tracked += 1;
  * bn_coef:     backward sums -> coef = [k1|k2|k3]; g_weight += sum dR*xhat, g_bias += sum dR.  Both zero `sums` on exit (the
- * accumulating kernels must start from zero).  n = elements per channel (B*T*E). */
+ * accumulating kernels must start from zero).  n = elements per channel (B*T*E).  Any C (one thread per channel). */
 int mmx_bn_finalize(double* sums, int C, double n, const float* w, const float* b, float* running_mean, float* running_var,
                     long long* num_batches_tracked, float momentum, float eps, float* bn, void* stream);
 int mmx_bn_coef(double* sums, int C, double n, const float* bn, float* coef, float* g_weight, float* g_bias, void* stream);

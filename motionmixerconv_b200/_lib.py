@@ -108,6 +108,14 @@ SIGNATURES = {
     "mmx_bn_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "mmx_bn_coef": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_ln_fwd": (C.c_int, [C.c_longlong, C.c_int, C.c_int] + [C.c_void_p] * 6),
+    "mmx_ln_bwd": (C.c_int, [C.c_longlong, C.c_int, C.c_int] + [C.c_void_p] * 9),
+    "mmx_bn1d_stats": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 3),
+    "mmx_bn1d_apply": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4),
+    "mmx_bn1d_bwd_reduce": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5),
+    "mmx_bn1d_bwd_apply": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6),
+    "mmx_se_res_fwd": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 7),
+    "mmx_se_res_bwd": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 9),
     "mmx_se_tail_fwd": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 5),
     "mmx_se_tail_bwd": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 8),
     "mmx_pose_encoder_fwd": (C.c_int, [C.POINTER(MmxEncoderDesc), C.POINTER(MmxEncoderParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -38,15 +38,15 @@ extern "C" int mmx_pck_hist(const float* pred, const float* gt, long long n_join
 extern "C" int mmx_bn_finalize(double* sums, int C, double n, const float* w, const float* b, float* running_mean, float* running_var,
                                long long* num_batches_tracked, float momentum, float eps, float* bn, void* stream) {
     if (!sums || !w || !b || !running_mean || !running_var || !num_batches_tracked || !bn) return fail(MMX_E_INVALID, "mmx_bn_finalize: null tensor");
-    if (C <= 0 || C > 32 || !(n >= 1.0)) return fail(MMX_E_INVALID, "mmx_bn_finalize: bad sizes");
+    if (C <= 0 || !(n >= 1.0)) return fail(MMX_E_INVALID, "mmx_bn_finalize: bad sizes");
     BnFinalizeArgs a; a.sums = sums; a.w = w; a.b = b; a.rm = running_mean; a.rv = running_var; a.nbt = num_batches_tracked; a.bn = bn;
     a.n = n; a.momentum = momentum; a.eps = eps; a.C = C;
-    return launch<BnFinalizeBody>(a, 1, 32, 16, stream, 1);
+    return launch<BnFinalizeBody>(a, (C + 31) / 32, 32, 16, stream, 1);
 }
 
 extern "C" int mmx_bn_coef(double* sums, int C, double n, const float* bn, float* coef, float* g_weight, float* g_bias, void* stream) {
     if (!sums || !bn || !coef || !g_weight || !g_bias) return fail(MMX_E_INVALID, "mmx_bn_coef: null tensor");
-    if (C <= 0 || C > 32 || !(n >= 1.0)) return fail(MMX_E_INVALID, "mmx_bn_coef: bad sizes");
+    if (C <= 0 || !(n >= 1.0)) return fail(MMX_E_INVALID, "mmx_bn_coef: bad sizes");
     BnCoefArgs a; a.sums = sums; a.bn = bn; a.coef = coef; a.gw = g_weight; a.gb = g_bias; a.n = n; a.C = C;
-    return launch<BnCoefBody>(a, 1, 32, 16, stream, 1);
+    return launch<BnCoefBody>(a, (C + 31) / 32, 32, 16, stream, 1);
 }

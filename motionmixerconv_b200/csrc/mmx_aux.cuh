@@ -93,8 +93,8 @@ struct BnFinalizeArgs {
 };
 MMX_D void bn_finalize_body(Exec& ex, const BnFinalizeArgs& a) {
     ex.phase([&](int tid) {
-        if (tid < a.C) {
-            const int c = tid, C = a.C;
+        const int c = ex.bid * ex.nthr + tid, C = a.C;
+        if (c < C) {
             const double mean = a.sums[c] / a.n;
             double var = a.sums[C + c] / a.n - mean * mean;
             if (var < 0.0) var = 0.0;
@@ -122,8 +122,8 @@ struct BnCoefArgs {
 };
 MMX_D void bn_coef_body(Exec& ex, const BnCoefArgs& a) {
     ex.phase([&](int tid) {
-        if (tid < a.C) {
-            const int c = tid, C = a.C;
+        const int c = ex.bid * ex.nthr + tid, C = a.C;
+        if (c < C) {
             a.coef[c] = a.bn[c];
             a.coef[C + c] = (float)(a.sums[c] / a.n);
             a.coef[2 * C + c] = (float)(a.sums[C + c] / a.n);

@@ -194,6 +194,159 @@ def mlp_block(x, meta, params):
 
 
 # ------------------------------------------------------------------------------------------------
+# MixerBlock with BatchNorm1d inside the MLP blocks (regularization == -1, mlp_mixer.py:72-73, 88-94)
+# ------------------------------------------------------------------------------------------------
+class MlpBnBlock:
+    """Static buffers + the stage-kernel sequence of one MixerBlock whose MlpBlocks regularise with BatchNorm1d.
+
+    Batch statistics are global over the batch, so the block is a chain of stage kernels (include/mmx.h, csrc/mmx_api_bnmlp.cu)
+    with a reduction between them; this class owns the saved tensors and is used both by the autograd Function below (fresh
+    buffers per call) and by TrainStep (static buffers inside the captured graph).  Token MLP: BatchNorm1d(hidden_dim) on
+    [B,H,*]; channel MLP: BatchNorm1d(seq_len) on [B,T,*]; reg1 after the activation, reg2 after fc2 (mlp_mixer.py:88-94).
+
+    ``params`` = MixerBlock.kernel_params() (14, SE weights may be None); ``bns`` = the four BatchNorm1d modules in execution
+    order (token reg1, token reg2, channel reg1, channel reg2).
+    """
+
+    def __init__(self, B, T, H, tok, ch, device, need_backward=True):
+        e = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=device)
+        self.B, self.T, self.H, self.tok, self.ch = B, T, H, tok, ch
+        self.nT, self.st1 = e(B, H, T), e(B * T, 2)
+        self.u1, self.g1, self.v1 = e(B, H, tok), e(B, H, tok), e(B, H, T)
+        self.x1 = e(B, T, H)
+        self.n2, self.st2 = e(B, T, H), e(B * T, 2)
+        self.u2, self.g2, self.v2 = e(B, T, ch), e(B, T, ch), e(B, T, H)
+        self.bn = [torch.zeros(4 * c, dtype=torch.float32, device=device) for c in (H, H, T, T)]
+        self.sums = torch.zeros(2 * max(H, T), dtype=torch.float64, device=device)
+        self.trained = True
+        if need_backward:
+            self.coef = e(3 * max(H, T))
+            self.dA, self.dC = e(B * T * H), e(B, T, H)
+            self.dB = e(max(B * T * ch, B * H * tok))
+
+    # channels / elements-per-channel of the four BatchNorm layers: (N, C, L, act?)
+    def _geo(self, i):
+        B, T, H, tok, ch = self.B, self.T, self.H, self.tok, self.ch
+        return [(B, H, tok), (B, H, T), (B, T, ch), (B, T, H)][i]
+
+    def _bn_vectors(self, i, u, act, bnm, training):
+        """per-channel vectors of BatchNorm layer i for the tensor u (pre-activation when act >= 0)."""
+        N, Cn, Ln = self._geo(i)
+        st = _stream()
+        if training:
+            _call("mmx_bn1d_stats", N, Cn, Ln, act, _p(u), _p(self.sums), st)
+            _call("mmx_bn_finalize", _p(self.sums), Cn, float(N * Ln), _p(bnm.weight), _p(bnm.bias), _p(bnm.running_mean), _p(bnm.running_var),
+                  _p(bnm.num_batches_tracked), float(bnm.momentum if bnm.momentum is not None else 0.1), float(bnm.eps), _p(self.bn[i]), st)
+        else:
+            with torch.no_grad():
+                xs = torch.rsqrt(bnm.running_var + bnm.eps)
+                scale = bnm.weight.detach() * xs
+                self.bn[i].copy_(torch.cat([scale, bnm.bias.detach() - bnm.running_mean * scale, xs, -bnm.running_mean * xs]))
+        return self.bn[i]
+
+    def forward(self, x, out, params, bns, act, se_hidden, use_max, training):
+        (ln1w, ln1b, tw1, tb1, tw2, tb2, ln2w, ln2b, cw1, cb1, cw2, cb2, s1, s2) = params
+        B, T, H, tok, ch = self.B, self.T, self.H, self.tok, self.ch
+        st = _stream()
+        a = L.MMX_ACT[act]
+        self.trained = bool(training)
+        # ---- token half: x1 = x + SE(BN(fc2(BN(act(fc1(LN1(x)^T)))))^T)
+        _call("mmx_ln_fwd", B * T, H, T, _p(x), _p(ln1w), _p(ln1b), _p(self.nT), _p(self.st1), st)
+        _call("mmx_linear_fwd", B * H, T, tok, _p(self.nT), _p(tw1), _p(tb1), _p(self.u1), st)
+        bn = self._bn_vectors(0, self.u1, a, bns[0], training)
+        _call("mmx_bn1d_apply", B, H, tok, a, _p(self.u1), _p(bn), _p(self.g1), st)
+        _call("mmx_linear_fwd", B * H, tok, T, _p(self.g1), _p(tw2), _p(tb2), _p(self.v1), st)
+        bn = self._bn_vectors(1, self.v1, -1, bns[1], training)
+        _call("mmx_se_res_fwd", B, T, H, se_hidden, int(use_max), 1, 1, _p(x), _p(self.v1), _p(bn), _p(s1), _p(s2), _p(self.x1), st)
+        # ---- channel half: out = x1 + SE(BN(fc2(BN(act(fc1(LN2(x1)))))))
+        _call("mmx_ln_fwd", B * T, H, 0, _p(self.x1), _p(ln2w), _p(ln2b), _p(self.n2), _p(self.st2), st)
+        _call("mmx_linear_fwd", B * T, H, ch, _p(self.n2), _p(cw1), _p(cb1), _p(self.u2), st)
+        bn = self._bn_vectors(2, self.u2, a, bns[2], training)
+        _call("mmx_bn1d_apply", B, T, ch, a, _p(self.u2), _p(bn), _p(self.g2), st)
+        _call("mmx_linear_fwd", B * T, ch, H, _p(self.g2), _p(cw2), _p(cb2), _p(self.v2), st)
+        bn = self._bn_vectors(3, self.v2, -1, bns[3], training)
+        _call("mmx_se_res_fwd", B, T, H, se_hidden, int(use_max), 0, 0, _p(self.x1), _p(self.v2), _p(bn), _p(s1), _p(s2), _p(out), st)
+        return out
+
+    def _bn_backward(self, i, u, act, d, gw, gb):
+        """d (gradient wrt the BatchNorm output, [N,C,L]) -> gradient wrt u, in place; gw / gb accumulated."""
+        N, Cn, Ln = self._geo(i)
+        st = _stream()
+        _call("mmx_bn1d_bwd_reduce", N, Cn, Ln, act, _p(u), _p(self.bn[i]), _p(d), _p(self.sums), st)
+        _call("mmx_bn_coef", _p(self.sums), Cn, float(N * Ln), _p(self.bn[i]), _p(self.coef), _p(gw), _p(gb), st)
+        if not self.trained:               # eval mode: the statistics are constants, only the affine back-propagates
+            self.coef[Cn:3 * Cn].zero_()
+        _call("mmx_bn1d_bwd_apply", N, Cn, Ln, act, _p(u), _p(self.bn[i]), _p(self.coef), _p(d), _p(d), st)
+
+    def backward(self, x, dout, dx, params, grads, bn_grads, act, se_hidden, use_max):
+        """grads: tensors matching ``params`` (accumulated); bn_grads: [(d weight, d bias)] x 4 (accumulated)."""
+        (ln1w, ln1b, tw1, tb1, tw2, tb2, ln2w, ln2b, cw1, cb1, cw2, cb2, s1, s2) = params
+        (g_ln1w, g_ln1b, g_tw1, g_tb1, g_tw2, g_tb2, g_ln2w, g_ln2b, g_cw1, g_cb1, g_cw2, g_cb2, g_s1, g_s2) = grads
+        B, T, H, tok, ch = self.B, self.T, self.H, self.tok, self.ch
+        st = _stream()
+        a = L.MMX_ACT[act]
+        dA, dB, dC = self.dA, self.dB, self.dC
+        # ---- channel half
+        _call("mmx_se_res_bwd", B, T, H, se_hidden, int(use_max), 0, 0, _p(self.v2), _p(self.bn[3]), _p(s1), _p(s2), _p(dout),
+              _p(g_s1), _p(g_s2), _p(dA), st)
+        self._bn_backward(3, self.v2, -1, dA, *bn_grads[3])
+        _call("mmx_linear_bwd", B * T, ch, H, _p(self.g2), _p(cw2), _p(dA), _p(g_cw2), _p(g_cb2), _p(dB), st)
+        self._bn_backward(2, self.u2, a, dB, *bn_grads[2])
+        _call("mmx_linear_bwd", B * T, H, ch, _p(self.n2), _p(cw1), _p(dB), _p(g_cw1), _p(g_cb1), _p(dA), st)
+        _call("mmx_ln_bwd", B * T, H, 0, _p(self.x1), _p(self.st2), _p(ln2w), _p(dA), _p(dout), _p(dC), _p(g_ln2w), _p(g_ln2b), st)
+        # ---- token half (dC = gradient wrt x1)
+        _call("mmx_se_res_bwd", B, T, H, se_hidden, int(use_max), 1, 1, _p(self.v1), _p(self.bn[1]), _p(s1), _p(s2), _p(dC),
+              _p(g_s1), _p(g_s2), _p(dA), st)
+        self._bn_backward(1, self.v1, -1, dA, *bn_grads[1])
+        _call("mmx_linear_bwd", B * H, tok, T, _p(self.g1), _p(tw2), _p(dA), _p(g_tw2), _p(g_tb2), _p(dB), st)
+        self._bn_backward(0, self.u1, a, dB, *bn_grads[0])
+        _call("mmx_linear_bwd", B * H, T, tok, _p(self.nT), _p(tw1), _p(dB), _p(g_tw1), _p(g_tb1), _p(dA), st)
+        _call("mmx_ln_bwd", B * T, H, T, _p(x), _p(self.st1), _p(ln1w), _p(dA), _p(dC), _p(dx), _p(g_ln1w), _p(g_ln1b), st)
+        return dx
+
+    n_launches_fwd = 16      # training mode: 2 LN + 4 fc + 4 x (stats, finalize) + 2 apply + 2 SE
+    n_launches_bwd = 22      # 2 SE + 4 x (reduce, coef, apply) + 4 fc + 2 LN
+
+
+class _MlpBlockBN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, meta, bns, *tensors):
+        x = _chk(x, "x")
+        params = [None if q is None else _chk(q, "parameter") for q in tensors[:14]]
+        tok, ch, se_hidden, act, use_se, use_max, training = meta[:7]
+        B, T, H = x.shape
+        needs_grad = any(ctx.needs_input_grad)
+        with torch.cuda.device_of(x):
+            run = MlpBnBlock(B, T, H, tok, ch, x.device, need_backward=needs_grad)
+            y = torch.empty_like(x)
+            run.forward(x, y, params, bns, act, se_hidden if use_se else 0, use_max, training)
+        ctx.run, ctx.params, ctx.x = run, params, x
+        ctx.cfg = (act, se_hidden if use_se else 0, use_max)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _chk(dy, "grad")
+        run, params, x = ctx.run, ctx.params, ctx.x
+        grads = _zeros_like_many(params)
+        bn_flat = _zeros_like_many([run.bn[i][:run.bn[i].numel() // 4] for i in range(4) for _ in range(2)])
+        bn_grads = [(bn_flat[2 * i], bn_flat[2 * i + 1]) for i in range(4)]
+        dx = torch.empty_like(x)
+        with torch.cuda.device_of(x):
+            run.backward(x, dy, dx, params, grads, bn_grads, *ctx.cfg)
+        ctx.run = None
+        return (dx, None, None, *grads, *bn_flat)
+
+
+def mlp_block_bn(x, meta, params, bns):
+    """MixerBlock forward with BatchNorm1d regularisation.  ``bns``: the four BatchNorm1d modules (token reg1, token reg2,
+    channel reg1, channel reg2); their weights / biases receive gradients, their running statistics are updated in training
+    mode exactly as nn.BatchNorm1d does (momentum, unbiased variance, num_batches_tracked)."""
+    bn_tensors = [t for m in bns for t in (m.weight, m.bias)]
+    return _MlpBlockBN.apply(x, meta, tuple(bns), *params, *bn_tensors)
+
+
+# ------------------------------------------------------------------------------------------------
 # MlpMixer head (mlp_mixer.py:332-335)
 # ------------------------------------------------------------------------------------------------
 _HEAD_FIELDS = ("ln_w", "ln_b", "wt", "bt", "wf", "bf")

@@ -60,7 +60,8 @@ class MlpBlock(nn.Module):
 
 
 class MixerBlock(nn.Module):
-    """One fused kernel forward, one backward (mlp_mixer.py:100-164)."""
+    """One fused kernel forward, one backward (mlp_mixer.py:100-164); with regularization == -1 (BatchNorm1d) a chain of stage
+    kernels around the batch reductions (functional.MlpBnBlock)."""
 
     def __init__(self, tokens_mlp_dim, channels_mlp_dim, seq_len, hidden_dim, activation='gelu', regularization=0,
                  initialization='none', r_se=4, use_max_pooling=False, use_se=True):
@@ -93,6 +94,11 @@ class MixerBlock(nn.Module):
         return [self.LN1.weight, self.LN1.bias, t.fc1.weight, t.fc1.bias, t.fc2.weight, t.fc2.bias,
                 self.LN2.weight, self.LN2.bias, c.fc1.weight, c.fc1.bias, c.fc2.weight, c.fc2.bias, *se]
 
+    def bn_modules(self):
+        """The four BatchNorm1d layers in execution order (regularization == -1)."""
+        t, c = self.mlp_block_token_mixing, self.mlp_block_channel_mixing
+        return [t.reg1, t.reg2, c.reg1, c.reg2]
+
     def meta(self, seed=0, step=0):
         p = self.regularization if self.regularization > 0.0 else 0.0
         return (self.tokens_mlp_dim, self.channels_mlp_dim, self.seq_len // self.r_se if self.use_se else 0,
@@ -100,10 +106,8 @@ class MixerBlock(nn.Module):
                 self.precision)
 
     def forward(self, x):
-        if self.regularization == -1.0:
-            raise NotImplementedError(
-                "MixerBlock with regularization=-1 (BatchNorm1d inside the MLPs) is not built yet: batch "
-                "statistics break the one-kernel-per-block fusion (see DESIGN.md, scope)")
+        if self.regularization == -1.0:          # BatchNorm1d inside the MLP blocks: a chain of stage kernels (batch statistics)
+            return F_.mlp_block_bn(x, self.meta(0, 0), self.kernel_params(), self.bn_modules())
         seed = step = 0
         if self.training and self.regularization > 0.0:
             seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF

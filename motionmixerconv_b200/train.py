@@ -83,11 +83,14 @@ class _MlpMixerPlan:
         self.dact = [torch.empty(B, T, H, device=dev) for _ in range(2)]
         self.step_dev = dropout_step_dev
         self.blocks = []
-        for mb in model.Mixer_Block:
-            if mb.regularization == -1.0:
-                raise NotImplementedError("TrainStep: BatchNorm (regularization=-1) MixerBlocks are not built yet")
+        self.bn_runs = {}                 # block index -> (MlpBnBlock, params, grads, bn modules, bn grads): regularization == -1
+        for i, mb in enumerate(model.Mixer_Block):
             kp = mb.kernel_params()
             self.blocks.append((mb, F_.mlp_block_table(kp), F_.mlp_block_table([flat.grad_of(q) for q in kp])))
+            if mb.regularization == -1.0:     # BatchNorm1d inside the MLP blocks: a chain of stage kernels with static buffers
+                bns = mb.bn_modules()
+                self.bn_runs[i] = (F_.MlpBnBlock(B, T, H, mb.tokens_mlp_dim, mb.channels_mlp_dim, dev), kp, [flat.grad_of(q) for q in kp],
+                                   bns, [(flat.grad_of(m.weight), flat.grad_of(m.bias)) for m in bns])
         hp = [model.LN.weight, model.LN.bias, model.conv_out.weight, model.conv_out.bias, model.fc_out.weight, model.fc_out.bias]
         self.head_w = F_.mlp_head_table(hp)
         self.head_g = F_.mlp_head_table([flat.grad_of(q) for q in hp])
@@ -99,11 +102,12 @@ class _MlpMixerPlan:
         self.n_launches_bwd = 2 + model.num_blocks
         # kernels that can save the token-half output x1 (+ SE gates) for the backward (the tcgen05 family): one extra tile per block
         lib = L.load()
-        self.saves = [bool(lib.mmx_mlp_block_saves(C.byref(self._desc(mb, True)))) for mb, _, _ in self.blocks]
+        self.saves = [i not in self.bn_runs and bool(lib.mmx_mlp_block_saves(C.byref(self._desc(mb, True)))) for i, (mb, _, _) in enumerate(self.blocks)]
         self.x1 = [torch.empty(B, T, H, device=dev) if s else None for s in self.saves]
         self.gate = [torch.empty(B, T, device=dev) if s else None for s in self.saves]
-        self.n_launches_fwd = 2 + sum(2 if s else 1 for s in self.saves)      # tcgen05 family: token half + channel half
-        self.n_launches_bwd = 2 + sum(2 if s else 1 for s in self.saves)
+        nb = len(self.bn_runs)
+        self.n_launches_fwd = 2 + sum(2 if s else 1 for s in self.saves) - nb + nb * F_.MlpBnBlock.n_launches_fwd   # tcgen05 family: token half + channel half
+        self.n_launches_bwd = 2 + sum(2 if s else 1 for s in self.saves) - nb + nb * F_.MlpBnBlock.n_launches_bwd
 
     def _desc(self, mb, training):
         m = mb.meta(self.seed, 0)
@@ -116,6 +120,11 @@ class _MlpMixerPlan:
         prec = L.MMX_PREC[md.precision or F_.get_precision()]
         L.check(lib, lib.mmx_linear_fwd_prec(self.B * T, D, H, _p(self.x), _p(self.conv_w), _p(self.conv_b), _p(self.acts[0]), prec, st), "mmx_linear_fwd")
         for i, (mb, tw, _) in enumerate(self.blocks):
+            if i in self.bn_runs:
+                run, kp, _, bns, _ = self.bn_runs[i]
+                m = mb.meta(0, 0)
+                run.forward(self.acts[i], self.acts[i + 1], kp, bns, m[3], m[2] if m[4] else 0, m[5], training)
+                continue
             d = self._desc(mb, training)
             if training and self.saves[i]:
                 L.check(lib, lib.mmx_mlp_block_fwd_save(C.byref(d), C.byref(tw), _p(self.acts[i]), _p(self.acts[i + 1]), _p(self.x1[i]),
@@ -135,6 +144,12 @@ class _MlpMixerPlan:
         for i in reversed(range(len(self.blocks))):
             mb, tw, tg = self.blocks[i]
             nxt = self.dact[1] if cur is self.dact[0] else self.dact[0]
+            if i in self.bn_runs:
+                run, kp, kg, _, bg = self.bn_runs[i]
+                m = mb.meta(0, 0)
+                run.backward(self.acts[i], cur, nxt, kp, kg, bg, m[3], m[2] if m[4] else 0, m[5])
+                cur = nxt
+                continue
             d = self._desc(mb, True)
             if self.saves[i]:
                 L.check(lib, lib.mmx_mlp_block_bwd_saved(C.byref(d), C.byref(tw), C.byref(tg), _p(self.acts[i]), _p(self.x1[i]), _p(self.gate[i]),

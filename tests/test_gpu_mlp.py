@@ -141,3 +141,101 @@ def test_large_batch_size_independent_properties():
     assert abs(l_all - 0.5 * (l_a + l_b)) <= 1e-5 * abs(l_all)
     err = (g_all - 0.5 * (g_a + g_b)).abs().max().item() / g_all.abs().max().item()
     assert err < 2e-5, err
+
+
+# ---- BatchNorm1d inside the MLP blocks (regularization == -1; mlp_mixer.py:72-73, sampled by optuna_search/optuna_main.py:189-190)
+def test_batchnorm_golden_train_and_eval():
+    g = Golden("mlp_bn")
+    model = _model(g.cfg, g.params).train()
+    pred, loss, grads, dx = _run(model, g.x, g.gt)
+    o64 = O.MlpMixerOracle(g.cfg, g.params, dtype=np.float64)
+    p64 = o64.forward(g.x)
+    _, dp64 = O.mpjpe(p64, g.gt.astype(np.float64))
+    g64, dx64 = o64.backward(dp64)
+    check_close("pred", pred, g.pred, p64, rtol=TOL)
+    assert abs(loss - g.loss) <= TOL * abs(g.loss)
+    floor = 5e-6 * grad_scale(g.grads)   # exactly-cancelling gradients (a bias in front of a BatchNorm) are pure rounding noise
+    for k, want in g.grads.items():
+        check_close("grad " + k, grads[k], want, g64[k], rtol=TOL, atol=floor)
+    check_close("dx", dx, g.dx, dx64, rtol=TOL, atol=1e-6 * float(np.abs(g.dx).max()))
+    sd = model.state_dict()
+    n_bn = 0
+    for k in sd:                                    # running statistics after ONE training forward == the reference's
+        if "running_" in k:
+            np.testing.assert_allclose(sd[k].cpu().numpy(), g.params1[k], rtol=1e-5, atol=1e-7, err_msg=k)
+            n_bn += 1
+        if "num_batches_tracked" in k:
+            assert int(sd[k]) == int(g.params[k]) + 1
+    assert n_bn == 2 * 4 * g.cfg["num_blocks"]
+    # eval mode uses the running statistics
+    ref = O.MlpMixerOracle(g.cfg, {k: v.cpu().numpy() for k, v in sd.items()}, dtype=np.float64)
+    pe64 = ref.forward(g.x, training=False)
+    model.eval()
+    with torch.no_grad():
+        pe = model(torch.from_numpy(g.x).cuda()).cpu().numpy()
+    check_close("pred_eval (after one update)", pe, pe64.astype(np.float32), pe64, rtol=TOL)
+    fresh = _model(g.cfg, g.params).eval()
+    with torch.no_grad():
+        pe0 = fresh(torch.from_numpy(g.x).cuda()).cpu().numpy()
+    check_close("pred_eval", pe0, g.pred_eval, rtol=TOL)
+
+
+@pytest.mark.parametrize("variant", ["mish_maxpool", "no_se_h50", "wide_B333"])
+def test_batchnorm_variants_vs_oracle(variant):
+    g = Golden("mlp_bn")
+    extra = {"mish_maxpool": dict(activation="mish", use_max_pooling=True, r_se=4),
+             "no_se_h50": dict(use_se=False, hidden_dim=50, channels_mlp_dim=44, tokens_mlp_dim=12),
+             "wide_B333": dict(hidden_dim=128, channels_mlp_dim=96)}[variant]
+    cfg = dict(g.cfg, **extra)
+    from motionmixerconv_b200.mlp_mixer import MlpMixer
+    torch.manual_seed(5)
+    model = MlpMixer(**cfg)
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if ".reg" in k:                          # non-trivial BatchNorm affine
+                p.add_(0.3 * torch.randn_like(p))
+    params = {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+    model = model.cuda().train()
+    B = 333 if variant == "wide_B333" else 37
+    x, gt = synthetic_pose_windows(B, cfg["seq_len"], cfg["pred_len"], cfg["input_size"], scale="amass", seed=3)
+    pred, loss, grads, dx = _run(model, x, gt)
+    res = {}
+    for dt in (np.float32, np.float64):
+        o = O.MlpMixerOracle(cfg, params, dtype=dt)
+        p = o.forward(x)
+        l, dp = O.mpjpe(p, gt.astype(dt))
+        gr, dxx = o.backward(dp)
+        res[dt] = (p, l, gr, dxx, o)
+    p32, l32, g32, dx32, _ = res[np.float32]
+    p64, l64, g64, dx64, o64 = res[np.float64]
+    check_close("pred", pred, p32, p64, rtol=TOL)
+    assert abs(loss - float(l64)) <= TOL * abs(float(l64))
+    floor = 5e-6 * grad_scale(g32)
+    for k in g32:
+        check_close("grad " + k, grads[k], g32[k], g64[k], rtol=TOL, atol=floor)
+    check_close("dx", dx, dx32, dx64, rtol=TOL, atol=1e-6 * float(np.abs(dx32).max()))
+    sd = model.state_dict()
+    for k in sd:
+        if "running_" in k:
+            np.testing.assert_allclose(sd[k].cpu().numpy(), o64.p[k], rtol=1e-5, atol=1e-7, err_msg=k)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_batchnorm_trainstep_three_adam_steps(use_graph):
+    from motionmixerconv_b200.train import TrainStep
+    g = Golden("mlp_bn")
+    model = _model(g.cfg, g.params).train()
+    ts = TrainStep(model, lr=1e-3, weight_decay=1e-5, use_cuda_graph=use_graph)
+    x, gt = torch.from_numpy(g.x).cuda(), torch.from_numpy(g.gt).cuda()
+    losses = [float(ts.step(x, gt)) for _ in range(3)]
+    np.testing.assert_allclose(losses, g.losses, rtol=5e-5)
+    sd = model.state_dict()
+    assert int(sd["Mixer_Block.0.mlp_block_token_mixing.reg1.num_batches_tracked"]) == 3
+    for k in g.params3:
+        if "running_" in k:
+            np.testing.assert_allclose(sd[k].cpu().numpy(), g.params3[k], rtol=2e-4, atol=1e-6, err_msg=k)
+        elif "num_batches" not in k:
+            np.testing.assert_allclose(sd[k].cpu().numpy(), g.params3[k], rtol=2e-3, atol=2e-5, err_msg=k)
+    p = ts.predict(x)                                 # eval semantics through the same plan: running statistics
+    ref = O.MlpMixerOracle(g.cfg, {k: v.cpu().numpy() for k, v in sd.items()}, dtype=np.float64)
+    check_close("predict", p.cpu().numpy(), ref.forward(g.x, training=False), rtol=TOL)
