@@ -478,7 +478,9 @@ def run_ours(args, w):
                          ("fp32 everywhere (north star: 1e-5 parity mode)" if prec == "fp32" else "tf32 requested; shape served by the fp32 kernels"),
             "l2": "512 MB L2 flush between timed iterations (outside the CUDA-event pairs)",
             "step": "CUDA graph A: memset + embed/encoder + block kernels fwd + head + mpjpe + head bwd + block kernels bwd + embed/encoder bwd"
-                    + ("; NCCL all-reduce of the flat gradient bucket" if world > 1 else "") + "; fused Adam",
+                    + ("; fused Adam" if world == 1 else
+                       ("; ONE kernel: all-reduce of the flat gradient bucket over NVLink peer memory + Adam (mmx_adam_step_peer), the whole step is one graph"
+                        if ts.peer is not None else "; NCCL all-reduce of the flat gradient bucket; fused Adam (graph B)")),
             "timing": "CUDA events around every step on the launching stream; value = B x steps / sum of the K step times (max over ranks); "
                       "ms_per_step_median = median of the K per-step times"},
         "e2e": {"value": world * B * args.steps / (t_e2e_ms * 1e-3), "unit": "sequences/s",

@@ -216,6 +216,11 @@ int mmx_conv_half_fwd(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, cons
 int mmx_conv_half_bwd(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, const MmxConvHalfParams* grads,
                       const float* x, const float* dy, float* dx, void* stream);
 
+/* Capability query: MMX_OK (+ sequences per CTA tile and dynamic shared memory of the plan) when mmx_conv_half_{fwd,bwd} serve
+ * this descriptor, otherwise the error code they would return (mmx_last_error() says why).  No launch.
+ * tools/conv_support_table.py tabulates the reference's Optuna grid (optuna_search/conv_optuna_main.py:339-342) with it. */
+int mmx_conv_half_plan(const MmxConvHalfDesc* d, int backward, int* seq_per_tile, int* smem_bytes);
+
 /* Training-mode BatchNorm2d between the activation and the SE layer (regularization == -1, conv_mixer_model.py:115-116,
  * 139-141) needs batch-global statistics, so a half runs as two passes each way; the per-channel vectors between the
  * passes are computed by the caller from the sums (a handful of C-element tensor ops):
@@ -305,6 +310,24 @@ int mmx_adam_step(float* p, const float* g, float* m, float* v, long long n, con
 /* Device-side optimiser clock: ++*step (DEVICE uint32, also the dropout step_dev); hyper[5], hyper[6] are
  * recomputed from hyper[1], hyper[2] and the new step.  Lets a CUDA graph replay a whole training step. */
 int mmx_adam_advance(float* hyper, unsigned int* step, void* stream);
+
+/* ---------------- data parallelism: gradient exchange fused into the optimiser (one process per GPU, one node) ----------------
+ * The reference trains on one device; the north star asks for batch-sharded data parallelism with one bucketed gradient
+ * all-reduce.  mmx_adam_step_peer is that all-reduce AND mmx_adam_step in one kernel over NVLink peer memory: every rank's flat
+ * gradient bucket lives in an allocation made by mmx_peer_alloc (cudaMalloc, zeroed; bucket first, then mmx_peer_flag_bytes(world)
+ * bytes of flags), exported with mmx_ipc_export (64-byte cudaIpcMemHandle_t), exchanged by the caller (torch.distributed) and
+ * mapped by every peer with mmx_ipc_open.  peer_g / peer_flags: DEVICE arrays [world] of the bucket / flag-block addresses of
+ * every rank as mapped in THIS process (own rank: the local pointer).  Sums in rank order on every rank (replicas stay
+ * bit-identical); hyper as mmx_adam_step (hyper[7] = 1/world); epoch: DEVICE uint32[2], zero-initialised, owned by the kernel.
+ * Collective: every rank must launch it the same number of times.  Waits are bounded (~15 s; then mmx_tc5_abort_count() > 0). */
+int mmx_peer_flag_bytes(int world);
+int mmx_peer_alloc(long long bytes, void** ptr);
+int mmx_peer_free(void* ptr);
+int mmx_ipc_export(void* ptr, unsigned char* handle64);
+int mmx_ipc_open(const unsigned char* handle64, void** ptr);
+int mmx_ipc_close(void* ptr);
+int mmx_adam_step_peer(float* p, float* m, float* v, const void* peer_g, const void* peer_flags, int rank, int world, long long n,
+                       const float* hyper, unsigned int* epoch, void* stream);
 
 #ifdef __cplusplus
 }

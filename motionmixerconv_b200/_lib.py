@@ -101,6 +101,7 @@ SIGNATURES = {
     "mmx_conv_half_fwd": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_conv_half_bwd": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams), C.POINTER(MmxConvHalfParams),
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_conv_half_plan": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.c_int, C.c_void_p, C.c_void_p]),
     "mmx_conv_half_bn_stats": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_conv_half_bn_apply": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams)] + [C.c_void_p] * 5),
     "mmx_conv_half_bn_bwd1": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams), C.POINTER(MmxConvHalfParams)] + [C.c_void_p] * 6),
@@ -129,6 +130,14 @@ SIGNATURES = {
     "mmx_pck_hist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mmx_mpjpe_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p]),
     "mmx_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "mmx_peer_flag_bytes": (C.c_int, [C.c_int]),
+    "mmx_peer_alloc": (C.c_int, [C.c_longlong, C.POINTER(C.c_void_p)]),
+    "mmx_peer_free": (C.c_int, [C.c_void_p]),
+    "mmx_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "mmx_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mmx_ipc_close": (C.c_int, [C.c_void_p]),
+    "mmx_adam_step_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_adam_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -105,6 +105,17 @@ extern "C" int mmx_conv_half_fwd(const MmxConvHalfDesc* d, const MmxConvHalfPara
     return d->act == MMX_ACT_GELU ? dispatch<ACT_GELU>(a, grid, smem, stream) : dispatch<ACT_MISH>(a, grid, smem, stream);
 }
 
+// capability query: does the fused half kernel serve this descriptor (forward / backward)?  MMX_OK + the plan, or the error the
+// compute entry point would return.  No launch; the ConvMixer module uses it to report unsupported shapes at construction.
+extern "C" int mmx_conv_half_plan(const MmxConvHalfDesc* d, int backward, int* seq_per_tile, int* smem_bytes) {
+    ConvDims m; size_t smem; int grid;
+    int rc = plan_conv_half(d, backward != 0, &m, &smem, &grid);
+    if (rc) return rc;
+    if (seq_per_tile) *seq_per_tile = m.S;
+    if (smem_bytes) *smem_bytes = (int)smem;
+    return MMX_OK;
+}
+
 extern "C" int mmx_se_tail_fwd(int B, int C, int T, int E, int se_hidden, int use_se, int use_max_pooling,
                                const float* se_w1, const float* se_w2, const float* x, float* y, void* stream) {
     if (!x || !y) return fail(MMX_E_INVALID, "mmx_se_tail_fwd: null tensor");

@@ -18,6 +18,8 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
+import sys
 
 import torch
 import torch.distributed as dist
@@ -56,7 +58,13 @@ class FlatBuffers:
                 view = self.p[off:off + p.numel()].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
-                self.grad_views[id(p)] = self.g[off:off + p.numel()].view(p.shape)
+        self.rebind_grads(self.g)
+
+    def rebind_grads(self, g):
+        """Use ``g`` (flat fp32, same length) as the gradient bucket: e.g. IPC-shared memory for the peer all-reduce."""
+        assert g.numel() == self.numel and g.dtype == torch.float32
+        self.g = g
+        self.grad_views = {id(p): g[off:off + p.numel()].view(p.shape) for p, off in zip(self.params, self.offsets)}
 
     def grad_of(self, p):
         return None if p is None else self.grad_views[id(p)]
@@ -324,6 +332,17 @@ class TrainStep:
             dist.broadcast(self.flat.p, src=src, group=process_group)
             for b in model.buffers():
                 dist.broadcast(b, src=src, group=process_group)
+        # gradient exchange: by default ONE kernel does the all-reduce over NVLink peer memory and the Adam update
+        # (mmx_adam_step_peer); MMX_DP_PEER=0, or peers that cannot be mapped, fall back to an NCCL all-reduce + mmx_adam_step
+        self.peer = None
+        if self.world > 1 and dev.type == "cuda" and os.environ.get("MMX_DP_PEER", "1") != "0":
+            try:
+                self.peer = P_.PeerGradBucket(self.flat.numel, dev, process_group)
+                self.flat.rebind_grads(self.peer.g)
+            except Exception as exc:                         # noqa: BLE001 -- any failure here means "use NCCL"
+                self.peer = None
+                if self.rank == 0:
+                    print("TrainStep: peer-memory gradient exchange unavailable (%s); using the NCCL all-reduce" % exc, file=sys.stderr)
         self._staged, self._copy_stream = None, None      # double-buffered host->device prefetch (step(..., prefetch=...))
 
     # ---- pieces -------------------------------------------------------------------------------
@@ -342,7 +361,15 @@ class TrainStep:
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         f = self.flat
         L.check(self.lib, self.lib.mmx_adam_advance(_p(self.hyper), _p(self.step_dev), st), "mmx_adam_advance")
-        L.check(self.lib, self.lib.mmx_adam_step(_p(f.p), _p(f.g), _p(f.m), _p(f.v), f.numel, _p(self.hyper), st), "mmx_adam_step")
+        if self.peer is not None:      # all-reduce over peer memory + Adam, one kernel (collective across the ranks)
+            self.peer.adam_step(f.p, f.m, f.v, self.hyper, st)
+        else:
+            L.check(self.lib, self.lib.mmx_adam_step(_p(f.p), _p(f.g), _p(f.m), _p(f.v), f.numel, _p(self.hyper), st), "mmx_adam_step")
+
+    def _exchange(self):
+        """NCCL path only: the peer kernel does the exchange inside _adam."""
+        if self.world > 1 and self.peer is None:
+            P_.allreduce_bucket(self.flat.g, self.pg)
 
     def _select_plan(self, B):
         """Make the plan (static activations, pointer tables, captured graphs) of batch size B current."""
@@ -465,16 +492,14 @@ class TrainStep:
         pl = self.plan
         if not self.use_graph:
             self._fwd_bwd()
-            if self.world > 1:
-                P_.allreduce_bucket(self.flat.g, self.pg)
+            self._exchange()
             self._adam()
         else:
             if self.graph_a is None:
                 self._capture()
             self.graph_a.replay()
-            if self.graph_b is not None:          # two-graph form: eager all-reduce between backward and Adam
-                if self.world > 1:
-                    P_.allreduce_bucket(self.flat.g, self.pg)
+            if self.graph_b is not None:          # two-graph form (NCCL path): eager all-reduce between backward and Adam
+                self._exchange()
                 self.graph_b.replay()
         n_joints = pl.pred.numel() // 3
         return (self.loss_sum * (float(self.loss_scale) / n_joints)).reshape(())
@@ -506,27 +531,24 @@ class TrainStep:
         saved = [b.clone() for b in state]
         with torch.cuda.stream(s):
             self._fwd_bwd()
-            if self.world > 1:
-                P_.allreduce_bucket(self.flat.g, self.pg)      # also initialises the NCCL communicator before any capture
+            self._exchange()                                   # NCCL path: also initialises the communicator before any capture
             self._adam()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize(self.device)
         with torch.no_grad():
             for b, sv in zip(state, saved):
                 b.copy_(sv)
-        import os
         # data parallel: the NCCL all-reduce CAN be captured into the same graph (MMX_DP_GRAPH_ALLREDUCE=1), but measured on
         # 8 x B200 the captured collective has a heavy tail (median step 0.918 ms, mean 1.55 ms) while the eager call between
         # two graphs is steady (0.914 / 0.914 ms): two graphs + eager all-reduce is the default
-        one_graph = self.world == 1 or os.environ.get("MMX_DP_GRAPH_ALLREDUCE", "0") == "1"
+        one_graph = self.world == 1 or self.peer is not None or os.environ.get("MMX_DP_GRAPH_ALLREDUCE", "0") == "1"
         self.graph_a = torch.cuda.CUDAGraph()
         if one_graph:
             # ONE graph per step: forward, backward, the NCCL all-reduce of the flat gradient bucket (NCCL collectives are
             # capturable) and the fused Adam -- no host round trip between backward, the collective and the optimizer
             with torch.cuda.graph(self.graph_a):
                 self._fwd_bwd()
-                if self.world > 1:
-                    P_.allreduce_bucket(self.flat.g, self.pg)
+                self._exchange()
                 self._adam()
             self.graph_b = None
         else:

@@ -148,3 +148,46 @@ def test_predict_and_step_interleave_at_different_batch_sizes():
     ts.model.train()
     with pytest.raises(RuntimeError):
         ts.step(x[:, :9], gt)                        # wrong frame count: rejected on the host, no out-of-bounds device write
+
+
+def test_peer_adam_kernel_world_of_one_equals_the_plain_adam_kernel():
+    """mmx_adam_step_peer (all-reduce over peer memory fused into Adam, csrc/mmx_api_peer.cu) with a world of one rank: the
+    flag protocol runs against the rank's own flag block, the bucket lives in an mmx_peer_alloc'ed allocation, and the update
+    must equal mmx_adam_step bit for bit over several replays (the epoch advances on the device).  The multi-rank behaviour is
+    checked by tools/dp_check.py on 2 / 8 GPUs (profiles/)."""
+    import ctypes as C
+    from motionmixerconv_b200 import _lib as L
+    from motionmixerconv_b200.parallel import _RawDeviceArray
+    lib = L.load()
+    n = 30000 + 4 * 7
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    flag_bytes = lib.mmx_peer_flag_bytes(1)
+    g_bytes = (n * 4 + 255) // 256 * 256
+    ptr = C.c_void_p()
+    L.check(lib, lib.mmx_peer_alloc(g_bytes + flag_bytes, C.byref(ptr)), "mmx_peer_alloc")
+    handle = C.create_string_buffer(64)
+    L.check(lib, lib.mmx_ipc_export(ptr.value, handle), "mmx_ipc_export")
+    assert any(handle.raw)
+    raw = _RawDeviceArray(ptr.value, n)
+    g = torch.as_tensor(raw, device="cuda")
+    peer_g = torch.tensor([ptr.value], dtype=torch.int64, device="cuda")
+    peer_f = torch.tensor([ptr.value + g_bytes], dtype=torch.int64, device="cuda")
+    epoch = torch.zeros(2, dtype=torch.int32, device="cuda")
+    torch.manual_seed(0)
+    pa = torch.randn(n, device="cuda")
+    pb = pa.clone()
+    ma, va, mb, vb = (torch.zeros(n, device="cuda") for _ in range(4))
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 1e-5, 1.0, 1.0, 1.0, 1 - 0.9, 1 - 0.999], dtype=torch.float32, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for it in range(5):
+        g.copy_(torch.randn(n, device="cuda"))
+        L.check(lib, lib.mmx_adam_advance(hyper.data_ptr(), step.data_ptr(), st), "advance")
+        L.check(lib, lib.mmx_adam_step(pa.data_ptr(), g.data_ptr(), ma.data_ptr(), va.data_ptr(), n, hyper.data_ptr(), st), "adam")
+        L.check(lib, lib.mmx_adam_step_peer(pb.data_ptr(), mb.data_ptr(), vb.data_ptr(), peer_g.data_ptr(), peer_f.data_ptr(), 0, 1, n,
+                                            hyper.data_ptr(), epoch.data_ptr(), st), "adam_peer")
+        torch.cuda.synchronize()
+        assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb), it
+        assert int(epoch[0]) == it + 1 and int(epoch[1]) == 0
+    assert lib.mmx_tc5_abort_count() == 0
+    del g, raw
+    L.check(lib, lib.mmx_peer_free(ptr.value), "mmx_peer_free")

@@ -39,7 +39,7 @@ for use_graph in (False, True):
     torch.manual_seed(100 + rank)                    # DIFFERENT initial weights per rank: the constructor broadcast must fix that
     model = MlpMixer(**cfg).to(dev).train().set_precision(prec)
     ts = TrainStep(model, lr=1e-3, weight_decay=1e-5, process_group=dist.group.WORLD, use_cuda_graph=use_graph)
-    log("TrainStep built (graph=%s)" % use_graph)
+    log("TrainStep built (graph=%s, gradient exchange: %s)" % (use_graph, "peer-memory all-reduce fused into Adam" if ts.peer is not None else "NCCL all-reduce"))
     lo, hi = rank * Bper, (rank + 1) * Bper
     for i in range(steps):
         loss = ts.step(xs[lo:hi], gts[lo:hi])
@@ -59,7 +59,10 @@ for use_graph in (False, True):
     upd = (ts.flat.p - ts1.flat.p).abs().max().item()
     moved = steps * 1e-3
     log("graph=%s identical_across_ranks=%s max|p_dp - p_single| = %.3e (weights moved by ~%.0e)" % (use_graph, ident, upd, moved))
-    ok = ok and ident and upd < 0.02 * moved
+    from motionmixerconv_b200 import _lib as L_
+    aborts = L_.load().mmx_tc5_abort_count()
+    log("timed-out waits: %d" % aborts)
+    ok = ok and ident and upd < 0.02 * moved and aborts == 0
     ts.release_graphs()
 dist.barrier(device_ids=[local])
 if rank == 0:
