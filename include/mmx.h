@@ -303,6 +303,10 @@ int mmx_pck_hist(const float* pred, const float* gt, long long n_joints, const f
 int mmx_mpjpe_fwd_bwd(const float* pred, const float* gt, float* dpred, float* loss_sum, long long n_joints,
                       float gscale, void* stream);
 
+/* Joint-angle loss (train_mixer_h36m.py:187, train_autoreg_mixer_h36m.py:209-210): mean over the rows of sum_d |pred - gt|.
+ * *loss_sum += sum |pred - gt| (caller zeroes it; mean = loss_sum / rows); dpred (nullable) = gscale * sign(pred - gt) / rows. */
+int mmx_l1_fwd_bwd(const float* pred, const float* gt, float* dpred, float* loss_sum, long long rows, int D, float gscale, void* stream);
+
 /* torch.optim.Adam (coupled L2) on flat buffers — train_mixer_h36m.py:63,193.
  * hyper (DEVICE, 10 floats): lr, beta1, beta2, eps, weight_decay, 1-beta1^t, sqrt(1-beta2^t), grad_scale,
  * 1-beta1, 1-beta2 (the last two rounded once from double, as PyTorch does). */

@@ -129,6 +129,7 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_pck_hist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mmx_mpjpe_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p]),
+    "mmx_l1_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
     "mmx_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "mmx_peer_flag_bytes": (C.c_int, [C.c_int]),
     "mmx_peer_alloc": (C.c_int, [C.c_longlong, C.POINTER(C.c_void_p)]),

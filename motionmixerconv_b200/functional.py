@@ -421,6 +421,33 @@ def mpjpe_error(batch_pred, batch_gt):
     return _Mpjpe.apply(batch_pred, batch_gt)
 
 
+class _AngleL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, gt):
+        pred, gt = _chk(pred, "prediction"), _chk(gt, "target")
+        if pred.numel() != gt.numel() or gt.dim() < 1:
+            raise RuntimeError("angle_l1_error: shapes %s / %s do not match" % (tuple(pred.shape), tuple(gt.shape)))
+        D = gt.shape[-1]
+        rows = gt.numel() // D
+        loss_sum = torch.zeros(1, dtype=torch.float32, device=pred.device)
+        dpred = torch.empty_like(pred) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device_of(pred):
+            _call("mmx_l1_fwd_bwd", _p(pred), _p(gt), _p(dpred), _p(loss_sum), rows, D, 1.0, _stream())
+        ctx.save_for_backward(dpred)
+        return (loss_sum / rows).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dpred,) = ctx.saved_tensors
+        return dpred * g, None
+
+
+def angle_l1_error(pred, gt):
+    """The reference's joint-angle training loss, ``torch.mean(torch.sum(torch.abs(pred.reshape(-1, out_n, D) - gt), dim=2).view(-1))``
+    (train_mixer_h36m.py:187, train_autoreg_mixer_h36m.py:209-210), as one fused kernel (loss + dL/dpred).  ``gt``: [..., D]."""
+    return _AngleL1.apply(pred, gt)
+
+
 # ------------------------------------------------------------------------------------------------
 # ConvMixer (conv_mixer_model.py, positional_encoder.py)
 # ------------------------------------------------------------------------------------------------

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import torch
 
-from .functional import mpjpe_error
+from .functional import angle_l1_error, mpjpe_error
 
 
 def _windows(args):
@@ -34,8 +34,7 @@ def autoregressive_process_batch(batch, model, args, dim_used, teacher_forcing, 
     elif args.loss_type == 'mpjpe':
         loss_fct = lambda pred, gt, out_n: mpjpe_error(pred, gt)
     elif args.loss_type == 'angle':
-        loss_fct = lambda pred, gt, out_n: torch.mean(
-            torch.sum(torch.abs(pred.reshape(-1, out_n, len(dim_used)) - gt), dim=2).view(-1))
+        loss_fct = lambda pred, gt, out_n: angle_l1_error(pred.reshape(-1, out_n, len(dim_used)), gt)
     else:
         raise ValueError("unknown loss_type %s" % args.loss_type)
     full_sequence = batch[:, :args.input_n_dataset + args.output_n_dataset, dim_used].clone()

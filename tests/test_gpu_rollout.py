@@ -155,3 +155,40 @@ def test_rollout_trainer_cuda_graph_matches_eager_steps(teacher_forcing):
         else:
             assert torch.equal(a, b_), k                  # num_batches_tracked
     assert bad / tot <= 0.01, (bad, tot)
+
+
+def test_angle_l1_loss_kernel_and_rollout_with_the_angle_loss():
+    """loss_type == 'angle' (train_mixer_h36m.py:187, train_autoreg_mixer_h36m.py:209-210): the fused L1 kernel against the
+    reference's torch expression (value and gradient), and a teacher-forced rollout with it against the same rollout whose
+    loss is the torch expression on the same predictions."""
+    from motionmixerconv_b200.functional import angle_l1_error
+    from motionmixerconv_b200.rollout import autoregressive_process_batch
+    torch.manual_seed(3)
+    pred = torch.randn(37, 5, 48, device="cuda", requires_grad=True)
+    gt = torch.randn(37, 5, 48, device="cuda")
+    with torch.no_grad():
+        pred[0, 0, :4] = gt[0, 0, :4]                   # exact zeros: sign(0) = 0 as torch.abs' backward
+    want = torch.mean(torch.sum(torch.abs(pred.reshape(-1, 5, 48) - gt), dim=2).view(-1))
+    (gw,) = torch.autograd.grad(want, pred)
+    got = angle_l1_error(pred.reshape(-1, 5, 48), gt)
+    (gg,) = torch.autograd.grad(got, pred)
+    assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want))
+    assert torch.equal(gg, gw)
+    g = Golden("conv_k3")
+    seq = synthetic_full_windows(6, 35, 33, scale="ais", seed=17)
+    batch = torch.from_numpy(seq).cuda()
+    args = types.SimpleNamespace(**dict(vars(ARGS), loss_type="angle"))
+    dim_used = list(range(33))
+    model = _model(g.cfg, g.params).train()
+    loss, predict = autoregressive_process_batch(batch, model, args, dim_used, True)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    model.zero_grad()
+    torch_l1 = lambda p, t: torch.mean(torch.sum(torch.abs(p.reshape(-1, args.output_n_model, len(dim_used)) - t), dim=2).view(-1))
+    loss2, predict2 = autoregressive_process_batch(batch, model, args, dim_used, True, loss_fn=torch_l1)
+    loss2.backward()
+    assert abs(float(loss) - float(loss2)) <= 1e-5 * abs(float(loss2))
+    assert torch.equal(predict, predict2)
+    scale = max(p.grad.abs().max().item() for p in model.parameters())
+    for k, p in model.named_parameters():
+        assert (p.grad - grads[k]).abs().max().item() <= 2e-5 * scale, k       # same dL/dpred; the kernels' atomics reorder sums
