@@ -174,6 +174,19 @@ static int chan_dispatch_act(bool bwd, const MmxMlpBlockDesc* d, const chan::Cha
 }
 static int chan_dispatch(bool bwd, const MmxMlpBlockDesc* d, const chan::ChanArgs& c, void* stream) {
     if (kp_of(d) == 128) return mmx_chan_wide_run(bwd, d->act, &c, stream);
+    // H, ch <= 64: the streamed-weight design at operand width 64 leaves room for TWO CTAs per SM (256 TMEM columns, < 100 KB
+    // shared each, 64 registers).  Measured on B200 (block fwd / bwd, us): B = 4096, H = 50: 46 / 142 resident vs 47 / 154
+    // streamed (1.2 tiles per CTA: the second CTA only doubles the per-CTA flush); B = 16384: 138 / 485 vs 138 / 463;
+    // H = ch = 64 (operand width 80 in the resident plan): 83 / 215 vs 78 / 205.  So: streamed when the resident plan would
+    // need the 80-column operands, or when every CTA slot gets >= 4 tiles.  MMX_CHAN_STREAMED: bit 0 forward, bit 1 backward
+    // (default -1 = this policy).
+    if (d->H <= 64 && d->ch <= 64 && !(d->ch & 1)) {
+        const int forced = env_int("MMX_CHAN_STREAMED", -1);
+        const chan::Geo g = chan::make_geo(d->T, d->H, (d->H & 3) ? 2 : 4);
+        const int ntiles = (d->B + g.seq_per_tile - 1) / g.seq_per_tile;
+        const bool policy = kp_of(d) == 80 || (bwd && ntiles >= 8 * dev_info().sms);
+        if (forced >= 0 ? (forced & (bwd ? 2 : 1)) != 0 : policy) return mmx_chan_wide_run(bwd, d->act, &c, stream);
+    }
     return d->act == MMX_ACT_GELU ? chan_dispatch_act<ACT_GELU>(bwd, d, c, stream) : chan_dispatch_act<ACT_MISH>(bwd, d, c, stream);
 }
 

@@ -42,29 +42,38 @@ static int wide_workspace(const float* key, uint8_t** out) {
     return MMX_OK;
 }
 
-template <int ACT, int VEC>
+template <int ACT, int VEC, int KP>
 static int run_wide(bool bwd, const chan::ChanArgs& c, void* stream) {
     const DevInfo di = dev_info();
-    const size_t smem = chanw::wide_smem_bytes(c.T, c.H, VEC, bwd);
+    const size_t smem = chanw::wide_smem_bytes<KP>(c.T, c.H, VEC, bwd);
     if (smem > (size_t)di.max_smem) return fail(MMX_E_UNSUPPORTED, "wide channel half: tile does not fit shared memory (H=%d ch=%d)", c.H, c.ch);
     uint8_t* ws = nullptr;
     int rc = wide_workspace(c.w1, &ws);
     if (rc) return rc;
-    if ((rc = launch_tc5v(chanw::chan_prep_kernel, 32, 256, 0, stream, c, ws))) return rc;
+    if ((rc = launch_tc5v(chanw::chan_prep_kernel<KP>, KP <= 64 ? 8 : 32, 256, 0, stream, c, ws))) return rc;
     const chan::Geo g = chan::make_geo(c.T, c.H, VEC);
     const int ntiles = (c.B + g.seq_per_tile - 1) / g.seq_per_tile;
-    const int grid = imin(ntiles, di.sms);                   // 512 TMEM columns, ~205 KB shared: one CTA per SM
+    // KP = 128: 512 TMEM columns, ~205 KB shared -> one CTA per SM; KP = 64: 256 columns, < 100 KB -> two CTAs per SM
+    int per_sm = KP <= 64 ? imin(2, (int)((di.max_smem + 1024) / (smem + 1024))) : 1;
+    per_sm = imax(1, imin(per_sm, env_int("MMX_CHAN_CTAS", 2)));
+    const int grid = balanced_grid(ntiles, di.sms * per_sm);
     const uint8_t* wsc = ws;
-    return bwd ? launch_tc5v(chanw::chan_wide_bwd_kernel<ACT, VEC>, grid, chan::kThreadsChan, smem, stream, c, wsc)
-               : launch_tc5v(chanw::chan_wide_fwd_kernel<ACT, VEC>, grid, chan::kThreadsChan, smem, stream, c, wsc);
+    return bwd ? launch_tc5v(chanw::chan_wide_bwd_kernel<ACT, VEC, KP>, grid, chan::kThreadsChan, smem, stream, c, wsc)
+               : launch_tc5v(chanw::chan_wide_fwd_kernel<ACT, VEC, KP>, grid, chan::kThreadsChan, smem, stream, c, wsc);
 }
 
-// act: MMX_ACT_*; args: const chan::ChanArgs*
+template <int KP>
+static int run_wide_kp(bool bwd, int act, const chan::ChanArgs& c, void* stream) {
+    const bool vec4 = (c.H & 3) == 0;
+    if (act == MMX_ACT_GELU) return vec4 ? run_wide<ACT_GELU, 4, KP>(bwd, c, stream) : run_wide<ACT_GELU, 2, KP>(bwd, c, stream);
+    return vec4 ? run_wide<ACT_MISH, 4, KP>(bwd, c, stream) : run_wide<ACT_MISH, 2, KP>(bwd, c, stream);
+}
+
+// act: MMX_ACT_*; args: const chan::ChanArgs*.  Operand width 64 (H, ch <= 64: two CTAs per SM) or 128.
 int mmx_chan_wide_run(bool bwd, int act, const void* args, void* stream) {
     const chan::ChanArgs& c = *static_cast<const chan::ChanArgs*>(args);
     if ((c.H & 1) || (c.ch & 1) || c.H > chanw::KPW || c.ch > chanw::KPW) return fail(MMX_E_UNSUPPORTED, "wide channel half: H, ch even and <= %d", chanw::KPW);
-    const bool vec4 = (c.H & 3) == 0;
-    if (act == MMX_ACT_GELU) return vec4 ? run_wide<ACT_GELU, 4>(bwd, c, stream) : run_wide<ACT_GELU, 2>(bwd, c, stream);
-    return vec4 ? run_wide<ACT_MISH, 4>(bwd, c, stream) : run_wide<ACT_MISH, 2>(bwd, c, stream);
+    if (c.H <= 64 && c.ch <= 64) return run_wide_kp<64>(bwd, act, c, stream);
+    return run_wide_kp<128>(bwd, act, c, stream);
 }
 #endif

@@ -21,20 +21,23 @@ namespace chanw {
 using namespace tc5;
 using namespace chan;
 
-constexpr int KPW = 128;
-using PW = Plan<KPW>;
-constexpr uint32_t kWsBytes = 2 * PW::WBUF + KPW * 4;      // W1' planes | W2 planes | b1'
-constexpr uint32_t kSmallW = (6 * KPW + 2 * 32 * kMaxRR + 4 * kHalves * 128 + 64) * 4;   // c1f, c2, gamma2, db1, db2, spare | se1, se2 | exchange | barriers
+constexpr int KPW = 128;                                    // widest operand served
+template <int KP> constexpr uint32_t ws_bytes() { return 2 * Plan<KP>::WBUF + KP * 4; }      // W1' planes | W2 planes | b1'
+constexpr uint32_t kWsBytes = 2 * Plan<KPW>::WBUF + KPW * 4;                                  // allocation size (any KP <= KPW)
+template <int KP> constexpr uint32_t small_w() { return (6 * KP + 2 * 32 * kMaxRR + 4 * kHalves * 128 + 64) * 4; }   // c1f, c2, gamma2, db1, db2, spare | se1, se2 | exchange | barriers
 
 MMX_HD uint32_t stage_bytes_of(const Geo& g) { return ((uint32_t)g.tile_rows * g.pitch * 4u + 64u + 127u) / 128u * 128u; }
+template <int KP>
 MMX_HD size_t wide_smem_bytes(int T, int H, int vec, bool bwd) {
     const Geo g = make_geo(T, H, vec);
     const uint32_t st = stage_bytes_of(g);
-    const uint32_t buf = PW::BUF > st ? PW::BUF : st;
-    return 1024 + (bwd ? 2 * buf : buf + st) + PW::WBUF + kSmallW;
+    const uint32_t buf = Plan<KP>::BUF > st ? Plan<KP>::BUF : st;
+    return 1024 + (bwd ? 2 * buf : buf + st) + Plan<KP>::WBUF + small_w<KP>();
 }
 
+template <int KPW>
 struct CarveW {
+    using PW = Plan<KPW>;
     uint8_t *bufX, *bufY, *slot;
     float *S, *c1f, *c2, *gam, *db1, *db2, *se1, *se2, *ex;
     uint64_t* bars;
@@ -64,7 +67,9 @@ struct CarveW {
 
 // ------------------------------------------------------------------------------------------ weight preparation
 // ws: W1' (hi plane, lo plane) | W2 (hi, lo) | b1'   -- panel layout, KPW x KPW, zero padded
+template <int KPW>
 static __global__ void __launch_bounds__(256) chan_prep_kernel(const ChanArgs a, uint8_t* ws) {
+    using PW = Plan<KPW>;
     pdl_launch_dependents();
     pdl_wait();                // the previous kernel in the stream may still be reading the workspace
     const int H = a.H, ch = a.ch;
@@ -102,7 +107,8 @@ static __global__ void __launch_bounds__(256) chan_prep_kernel(const ChanArgs a,
 }
 
 // per-CTA constants that do not depend on the workspace.  Contains a CTA barrier.
-MMX_D void small_params(const ChanArgs& a, const CarveW& cv, int tid) {
+template <int KPW>
+MMX_D void small_params(const ChanArgs& a, const CarveW<KPW>& cv, int tid) {
     const int H = a.H, T = a.T, rr = a.rr;
     for (int c = tid; c < KPW; c += kThreadsChan) {
         cv.c2[c] = c < H ? a.b2[c] : 0.0f;
@@ -117,9 +123,10 @@ MMX_D void small_params(const ChanArgs& a, const CarveW& cv, int tid) {
     __syncthreads();
 }
 
+template <int KPW>
 MMX_D void load_weight(uint8_t* slot, const uint8_t* ws, int which, uint64_t* bar) {   // one thread
-    mbar_expect_tx(bar, PW::WBUF);
-    bulk_g2s(slot, ws + (size_t)which * PW::WBUF, PW::WBUF, bar);
+    mbar_expect_tx(bar, Plan<KPW>::WBUF);
+    bulk_g2s(slot, ws + (size_t)which * Plan<KPW>::WBUF, Plan<KPW>::WBUF, bar);
 }
 
 // column sums over the warp's 32 rows of an 8-column chunk: lanes with (lane & 3) == 0 return the total of column
@@ -149,7 +156,9 @@ MMX_D void col_accumulate(float* dst, int c8, const float (&v)[8], int lane) {
 }
 
 // xhat chunk from the operand's hi + lo planes (|error| <= 2^-17 |xhat|)
+template <int KPW>
 MMX_D void xhat_from_planes(const uint8_t* buf, int row, int c8, float (&xh)[8]) {
+    using PW = Plan<KPW>;
     const uint4 h = *reinterpret_cast<const uint4*>(buf + c8 * PW::PS + row * 16);
     const uint4 l = *reinterpret_cast<const uint4*>(buf + PW::PLANE + c8 * PW::PS + row * 16);
     const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
@@ -163,13 +172,12 @@ MMX_D void xhat_from_planes(const uint8_t* buf, int row, int c8, float (&xh)[8])
 // ==========================================================================================
 // forward
 // ==========================================================================================
-template <int ACT, int VEC>
-__global__ void __launch_bounds__(kThreadsChan) chan_wide_fwd_kernel(const ChanArgs a, const uint8_t* ws) {
-    constexpr int KP = KPW;
-    using P = PW;
+template <int ACT, int VEC, int KP>
+__global__ void __launch_bounds__(kThreadsChan, KP <= 64 ? 2 : 1) chan_wide_fwd_kernel(const ChanArgs a, const uint8_t* ws) {
+    using P = Plan<KP>;
     extern __shared__ uint8_t smem_raw[];
     const Geo g = make_geo(a.T, a.H, VEC);
-    const CarveW cv(smem_raw, g, false);
+    const CarveW<KP> cv(smem_raw, g, false);
     uint8_t* bufX = cv.bufX;
     float* S = cv.S;
     uint64_t* bars = cv.bars;
@@ -181,7 +189,8 @@ __global__ void __launch_bounds__(kThreadsChan) chan_wide_fwd_kernel(const ChanA
     const Dropout dr = resolve_dropout(a.dr);
     const uint32_t th16 = dr.thresh >> 16;
     const uint32_t key2 = drop_key(dr.seed_lo, dr.seed_hi, a.site_base + 2, dr.step), key3 = drop_key(dr.seed_lo, dr.seed_hi, a.site_base + 3, dr.step);
-    constexpr int TM_COLS = 512;
+    constexpr int TM_COLS = 4 * KP;      // U | Y | (residual rows resp. Wt) | dW2
+    static_assert(TM_COLS == 256 || TM_COLS == 512, "KP = 64 or 128");
     constexpr int NCH = KP / 8;
 
     if (tid == 0) {
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(kThreadsChan) chan_wide_fwd_kernel(const ChanA
     for (int c = tid; c < KP; c += kThreadsChan) cv.c1f[c] = reinterpret_cast<const float*>(ws + 2 * P::WBUF)[c];
     uint32_t ph_w = 0;
     if ((int)blockIdx.x < ntiles) {
-        if (tid == 0) load_weight(cv.slot, ws, 0, &bars[2]);
+        if (tid == 0) load_weight<KP>(cv.slot, ws, 0, &bars[2]);
         if (warp == 0) stage_in<VEC>(S, a.x1, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), a.H, g.pitch, &bars[0], lane);
     }
     fence_async_smem();
@@ -277,7 +286,7 @@ __global__ void __launch_bounds__(kThreadsChan) chan_wide_fwd_kernel(const ChanA
         mbar_wait(&bars[1], ph_mma, abortf);
         ph_mma ^= 1;
         tc_fence_after();
-        if (tid == 0) load_weight(cv.slot, ws, 1, &bars[2]);
+        if (tid == 0) load_weight<KP>(cv.slot, ws, 1, &bars[2]);
 #pragma unroll 1
         for (int c8 = half; c8 < NCH; c8 += kHalves) {
             float u[8], b[8];
@@ -307,7 +316,7 @@ __global__ void __launch_bounds__(kThreadsChan) chan_wide_fwd_kernel(const ChanA
         mbar_wait(&bars[1], ph_mma, abortf);
         ph_mma ^= 1;
         tc_fence_after();
-        if (tid == 0 && next < ntiles) load_weight(cv.slot, ws, 0, &bars[2]);
+        if (tid == 0 && next < ntiles) load_weight<KP>(cv.slot, ws, 0, &bars[2]);
         float ssum = 0.0f, dummy = 0.0f;
 #pragma unroll 1
         for (int c8 = half; c8 < nchH; c8 += kHalves) {
@@ -358,13 +367,12 @@ __global__ void __launch_bounds__(kThreadsChan) chan_wide_fwd_kernel(const ChanA
 // ==========================================================================================
 // backward (forward recomputed from x1)
 // ==========================================================================================
-template <int ACT, int VEC>
-__global__ void __launch_bounds__(kThreadsChan) chan_wide_bwd_kernel(const ChanArgs a, const uint8_t* ws) {
-    constexpr int KP = KPW;
-    using P = PW;
+template <int ACT, int VEC, int KP>
+__global__ void __launch_bounds__(kThreadsChan, KP <= 64 ? 2 : 1) chan_wide_bwd_kernel(const ChanArgs a, const uint8_t* ws) {
+    using P = Plan<KP>;
     extern __shared__ uint8_t smem_raw[];
     const Geo g = make_geo(a.T, a.H, VEC);
-    const CarveW cv(smem_raw, g, true);
+    const CarveW<KP> cv(smem_raw, g, true);
     uint8_t* bufX = cv.bufX;                  // xhat -> dY2 -> xhat again
     uint8_t* bufY = cv.bufY;                  // x1 tile (fp32) -> G2 -> dU2
     float* S1 = cv.S;
@@ -377,7 +385,8 @@ __global__ void __launch_bounds__(kThreadsChan) chan_wide_bwd_kernel(const ChanA
     const Dropout dr = resolve_dropout(a.dr);
     const uint32_t th16 = dr.thresh >> 16;
     const uint32_t key2 = drop_key(dr.seed_lo, dr.seed_hi, a.site_base + 2, dr.step), key3 = drop_key(dr.seed_lo, dr.seed_hi, a.site_base + 3, dr.step);
-    constexpr int TM_COLS = 512;
+    constexpr int TM_COLS = 4 * KP;      // U | Y | Wt | dW2
+    static_assert(TM_COLS == 256 || TM_COLS == 512, "KP = 64 or 128");
     constexpr int NCH = KP / 8;
     constexpr int CPT = NCH / kHalves;        // chunks per thread and pass
 
@@ -397,7 +406,7 @@ __global__ void __launch_bounds__(kThreadsChan) chan_wide_bwd_kernel(const ChanA
     for (int c = tid; c < KP; c += kThreadsChan) cv.c1f[c] = reinterpret_cast<const float*>(ws + 2 * P::WBUF)[c];
     uint32_t ph_w = 0;
     if ((int)blockIdx.x < ntiles) {
-        if (tid == 0) load_weight(cv.slot, ws, 0, &bars[2]);
+        if (tid == 0) load_weight<KP>(cv.slot, ws, 0, &bars[2]);
         if (warp == 0) stage_in<VEC>(S1, a.x1, (size_t)blockIdx.x * g.tile_rows, tile_nrows(blockIdx.x), a.H, g.pitch, &bars[0], lane);
     }
     fence_async_smem();
@@ -480,7 +489,7 @@ __global__ void __launch_bounds__(kThreadsChan) chan_wide_bwd_kernel(const ChanA
         mbar_wait(&bars[1], ph_mma, abortf);
         ph_mma ^= 1;
         tc_fence_after();
-        if (tid == 0) load_weight(cv.slot, ws, 1, &bars[2]);
+        if (tid == 0) load_weight<KP>(cv.slot, ws, 1, &bars[2]);
 #pragma unroll 1
         for (int c8 = half; c8 < NCH; c8 += kHalves) {
             float u[8], b[8], dact[8];
@@ -600,7 +609,7 @@ __global__ void __launch_bounds__(kThreadsChan) chan_wide_bwd_kernel(const ChanA
         mbar_wait(&bars[1], ph_mma, abortf);
         ph_mma ^= 1;
         tc_fence_after();
-        if (tid == 0) load_weight(cv.slot, ws, 0, &bars[2]);
+        if (tid == 0) load_weight<KP>(cv.slot, ws, 0, &bars[2]);
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
             const int c8 = half + kHalves * i;
@@ -646,7 +655,7 @@ __global__ void __launch_bounds__(kThreadsChan) chan_wide_bwd_kernel(const ChanA
                 const int c8 = half + kHalves * i;
                 float u[8];
                 tmem_ld8(tmem_addr(tU, qtr, 8 * c8), u);
-                xhat_from_planes(bufX, prow, c8, xv[i]);
+                xhat_from_planes<KP>(bufX, prow, c8, xv[i]);
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -676,27 +685,28 @@ __global__ void __launch_bounds__(kThreadsChan) chan_wide_bwd_kernel(const ChanA
 
     // ---------------- flush: Wt, dW2 (TMEM, lane = output row) -> global gradients
     if (!first) {
-        float* stg = reinterpret_cast<float*>(bufX);          // [128][128], columns rotated by the row (conflict-free stores)
+        float* stg = reinterpret_cast<float*>(bufX);          // [KP][KP], columns rotated by the row (conflict-free stores)
         tc_fence_after();
 #pragma unroll 1
         for (int c8 = half; c8 < NCH; c8 += kHalves) {
             float u[8];
             tmem_ld8(tmem_addr(tDW1, qtr, 8 * c8), u);
             tmem_wait_ld();
+            if (prow < KP)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) stg[prow * 128 + ((8 * c8 + j + prow) & 127)] = u[j];
+                for (int j = 0; j < 8; ++j) stg[prow * KP + ((8 * c8 + j + prow) & (KP - 1))] = u[j];
         }
         __syncthreads();
         for (int i = tid; i < ch * H; i += kThreadsChan) {
             const int c = i / H, h = i - c * H;
-            red_add(a.g_w1 + i, stg[c * 128 + ((h + c) & 127)] * cv.gam[h]);
+            red_add(a.g_w1 + i, stg[c * KP + ((h + c) & (KP - 1))] * cv.gam[h]);
         }
         for (int h = tid; h < H; h += kThreadsChan) {
             float sg = 0.0f, sb = 0.0f;
 #pragma unroll 8
             for (int c = 0; c < ch; ++c) {
                 const float w = a.w1[(size_t)c * H + h];
-                sg = fmaf(stg[c * 128 + ((h + c) & 127)], w, sg);
+                sg = fmaf(stg[c * KP + ((h + c) & (KP - 1))], w, sg);
                 sb = fmaf(cv.db1[c], w, sb);
             }
             red_add(a.g_ln_g + h, sg);
@@ -709,13 +719,14 @@ __global__ void __launch_bounds__(kThreadsChan) chan_wide_bwd_kernel(const ChanA
             float u[8];
             tmem_ld8(tmem_addr(tDW2, qtr, 8 * c8), u);
             tmem_wait_ld();
+            if (prow < KP)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) stg[prow * 128 + ((8 * c8 + j + prow) & 127)] = u[j];
+                for (int j = 0; j < 8; ++j) stg[prow * KP + ((8 * c8 + j + prow) & (KP - 1))] = u[j];
         }
         __syncthreads();
         for (int i = tid; i < H * ch; i += kThreadsChan) {
             const int h = i / ch, c = i - h * ch;
-            red_add(a.g_w2 + i, stg[h * 128 + ((c + h) & 127)]);
+            red_add(a.g_w2 + i, stg[h * KP + ((c + h) & (KP - 1))]);
         }
         for (int h = tid; h < H; h += kThreadsChan) red_add(a.g_b2 + h, cv.db2[h]);
         if (rr > 0) {
