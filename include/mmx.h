@@ -221,6 +221,29 @@ int mmx_conv_half_bwd(const MmxConvHalfDesc* d, const MmxConvHalfParams* w, cons
  * tools/conv_support_table.py tabulates the reference's Optuna grid (optuna_search/conv_optuna_main.py:339-342) with it. */
 int mmx_conv_half_plan(const MmxConvHalfDesc* d, int backward, int* seq_per_tile, int* smem_bytes);
 
+/* ---- large ConvMixerBlock halves: shapes whose tile does not fit the fused kernels (mmx_conv_half_plan says so: C = 8, E = 192 with
+ * 5x9 ... 9x29 kernels, most of optuna_search/conv_optuna_main.py:339-342), and BatchNorm with the max squeeze.  Same arithmetic as
+ * mmx_conv_half_{fwd,bwd}, as a chain of stage kernels with the intermediates in HBM (functional.ConvHalfLarge sequences them):
+ *   forward :  mmx_ln_fwd -> mmx_conv2d_large_fwd -> [mmx_bn1d_stats (act) + mmx_bn_finalize] -> mmx_conv_tail_fwd
+ *   backward:  mmx_conv_tail_bwd1 -> [mmx_bn_coef] -> mmx_conv_tail_bwd2 -> mmx_conv2d_large_fwd(data_gradient) + mmx_conv2d_large_wgrad
+ *              -> mmx_ln_bwd
+ * The descriptor is the half's MmxConvHalfDesc.  Dropout masks are those of the fused kernels. */
+/* out = conv2d(in) + bias (conv_mixer_model.py:133); data_gradient != 0: d(in) from d(out) (weights flipped / transposed, no bias) */
+int mmx_conv2d_large_fwd(const MmxConvHalfDesc* d, int data_gradient, const float* in, const float* w, const float* bias, float* out,
+                         void* stream);
+/* dw [C,C,kt,kp] += dz (*) n, db [C] += sum dz */
+int mmx_conv2d_large_wgrad(const MmxConvHalfDesc* d, const float* dz, const float* n, float* dw, float* db, void* stream);
+/* y = x + SE(reg(act(z))); reg = dropout of the descriptor, or (bn_aff != null) the BatchNorm affine [scale|shift][C] */
+int mmx_conv_tail_fwd(const MmxConvHalfDesc* d, const float* x, const float* z, const float* bn_aff, const float* se_w1, const float* se_w2,
+                      float* y, void* stream);
+/* SE backward: gd [B,T,3] = (gate, d squeeze, argmax), SE weight gradients accumulated; bn ([scale|shift|xs|xo][C]) != null:
+ * sums[0:C] += sum dR, sums[C:2C] += sum dR*xhat */
+int mmx_conv_tail_bwd1(const MmxConvHalfDesc* d, const float* z, const float* dy, const float* bn, const float* se_w1, const float* se_w2,
+                       float* g_se_w1, float* g_se_w2, float* gd, double* sums, void* stream);
+/* dz [B,C,T,E] (gradient wrt the conv output) from dy, gd and, BatchNorm, bn + coef */
+int mmx_conv_tail_bwd2(const MmxConvHalfDesc* d, const float* z, const float* dy, const float* gd, const float* bn, const float* coef,
+                       float* dz, void* stream);
+
 /* Training-mode BatchNorm2d between the activation and the SE layer (regularization == -1, conv_mixer_model.py:115-116,
  * 139-141) needs batch-global statistics, so a half runs as two passes each way; the per-channel vectors between the
  * passes are computed by the caller from the sums (a handful of C-element tensor ops):

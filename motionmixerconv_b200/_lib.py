@@ -102,6 +102,11 @@ SIGNATURES = {
     "mmx_conv_half_bwd": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams), C.POINTER(MmxConvHalfParams),
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_conv_half_plan": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.c_int, C.c_void_p, C.c_void_p]),
+    "mmx_conv2d_large_fwd": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.c_int] + [C.c_void_p] * 5),
+    "mmx_conv2d_large_wgrad": (C.c_int, [C.POINTER(MmxConvHalfDesc)] + [C.c_void_p] * 5),
+    "mmx_conv_tail_fwd": (C.c_int, [C.POINTER(MmxConvHalfDesc)] + [C.c_void_p] * 7),
+    "mmx_conv_tail_bwd1": (C.c_int, [C.POINTER(MmxConvHalfDesc)] + [C.c_void_p] * 10),
+    "mmx_conv_tail_bwd2": (C.c_int, [C.POINTER(MmxConvHalfDesc)] + [C.c_void_p] * 7),
     "mmx_conv_half_bn_stats": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mmx_conv_half_bn_apply": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams)] + [C.c_void_p] * 5),
     "mmx_conv_half_bn_bwd1": (C.c_int, [C.POINTER(MmxConvHalfDesc), C.POINTER(MmxConvHalfParams), C.POINTER(MmxConvHalfParams)] + [C.c_void_p] * 6),

@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from typing import Tuple, Union
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -172,13 +174,26 @@ class ConvMixerBlock(nn.Module):
         return (cb.kernel, cb.pad, self.in_nTP // self.r_se if self.use_se else 0, self.activation, self.use_se,
                 self.use_max_pooling, self.training, 2 * self.block_index + half, p, seed, step)
 
+    def uses_large_path(self, half, B):
+        """True when this half runs as the stage-kernel chain instead of one fused kernel per direction."""
+        if self.regularization == -1.0 and self.use_se and self.use_max_pooling:
+            return True
+        if os.environ.get("MMX_CONV_FORCE_LARGE", "0") == "1":     # tests: run any shape through the stage-kernel chain
+            return True
+        key = (half, B > 0)
+        cache = self.__dict__.setdefault("_fits", {})
+        if key not in cache:
+            cache[key] = F_.conv_half_fits(max(B, 1), self.conv_nChan, self.in_nTP, self.dimPosEmb, self.half_meta(half))
+        return not cache[key]
+
     def _half(self, x, half, seed, step):
         cb = self.conv1 if half == 0 else self.conv2
         meta, params = self.half_meta(half, seed, step), self.half_params(half)
+        if self.uses_large_path(half, x.shape[0]):
+            # shapes the fused kernels do not hold in shared memory (most of the Optuna grid at C = 8, E = 192) and BatchNorm
+            # with the max squeeze: the same arithmetic as a chain of stage kernels (functional.ConvHalfLarge)
+            return F_.conv_half_large(x, meta, params, cb.reg if self.regularization == -1.0 else None)
         if self.regularization == -1.0:
-            if self.use_se and self.use_max_pooling:
-                raise NotImplementedError("ConvMixerBlock: BatchNorm (regularization=-1) with use_max_pooling=True is not built "
-                                          "(the two-pass BatchNorm kernels implement the mean squeeze only)")
             if self.training:
                 return F_.conv_half_bn(x, meta, cb.reg, params)
             return F_.conv_half(x, meta, params, bn_aff=F_.bn_eval_affine(cb.reg))

@@ -617,6 +617,117 @@ def bn_eval_affine(bn_module):
     return torch.cat([scale, bn_module.bias.detach() - bn_module.running_mean * scale]).contiguous()
 
 
+# ---- large halves: shapes the fused kernels do not serve (mmx_conv_half_plan), BatchNorm with the max squeeze ----------------
+def conv_half_fits(B, C, T, E, meta):
+    """True when the fused half kernels (forward and backward) serve this shape; else the stage-kernel chain below runs."""
+    desc = conv_half_desc(B, C, T, E, *meta)
+    lib = L.load()
+    return lib.mmx_conv_half_plan(C_.byref(desc), 0, None, None) == 0 and lib.mmx_conv_half_plan(C_.byref(desc), 1, None, None) == 0
+
+
+class ConvHalfLarge:
+    """Static buffers + the stage-kernel sequence of one ConvMixerBlock half that does not fit the fused kernels (include/mmx.h,
+    csrc/mmx_api_conv_large.cu): LN -> conv2d -> [BatchNorm statistics] -> act / reg / SE / residual, intermediates in HBM.
+    Used by the autograd Function below (fresh buffers per call) and by TrainStep (static buffers inside the captured graph).
+    ``params`` = ConvMixerBlock.half_params(half); ``bn``: the half's BatchNorm2d module or None."""
+
+    def __init__(self, B, C, T, E, device, need_backward=True, with_bn=False):
+        e = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=device)
+        self.B, self.C, self.T, self.E = B, C, T, E
+        self.n, self.stats, self.z = e(B, C, T, E), e(B * C * T, 2), e(B, C, T, E)
+        self.bn = torch.zeros(4 * C, dtype=torch.float32, device=device) if with_bn else None
+        self.sums = torch.zeros(2 * C, dtype=torch.float64, device=device) if with_bn else None
+        self.trained = True
+        if need_backward:
+            self.gd, self.dz, self.dn = e(B, T, 3), e(B, C, T, E), e(B, C, T, E)
+            self.coef = e(3 * C) if with_bn else None
+
+    def forward(self, desc, x, y, params, bnm=None):
+        ln_w, ln_b, cw, cb, s1, s2 = params
+        B, Cn, T, E = self.B, self.C, self.T, self.E
+        st = _stream()
+        _call("mmx_ln_fwd", B * Cn * T, E, 0, _p(x), _p(ln_w), _p(ln_b), _p(self.n), _p(self.stats), st)
+        _call("mmx_conv2d_large_fwd", C_.byref(desc), 0, _p(self.n), _p(cw), _p(cb), _p(self.z), st)
+        aff = None
+        self.trained = bool(desc.training)
+        if bnm is not None:
+            if desc.training:
+                _call("mmx_bn1d_stats", B, Cn, T * E, desc.act, _p(self.z), _p(self.sums), st)
+                _call("mmx_bn_finalize", _p(self.sums), Cn, float(B * T * E), _p(bnm.weight), _p(bnm.bias), _p(bnm.running_mean),
+                      _p(bnm.running_var), _p(bnm.num_batches_tracked), float(bnm.momentum if bnm.momentum is not None else 0.1),
+                      float(bnm.eps), _p(self.bn), st)
+            else:
+                with torch.no_grad():
+                    xs = torch.rsqrt(bnm.running_var + bnm.eps)
+                    scale = bnm.weight.detach() * xs
+                    self.bn.copy_(torch.cat([scale, bnm.bias.detach() - bnm.running_mean * scale, xs, -bnm.running_mean * xs]))
+            aff = self.bn
+        _call("mmx_conv_tail_fwd", C_.byref(desc), _p(x), _p(self.z), _p(aff), _p(s1), _p(s2), _p(y), st)
+        return y
+
+    def backward(self, desc, x, dy, dx, params, grads, bn_grads=None):
+        ln_w, ln_b, cw, cb, s1, s2 = params
+        g_ln_w, g_ln_b, g_cw, g_cb, g_s1, g_s2 = grads
+        B, Cn, T, E = self.B, self.C, self.T, self.E
+        st = _stream()
+        bn = self.bn if bn_grads is not None else None
+        _call("mmx_conv_tail_bwd1", C_.byref(desc), _p(self.z), _p(dy), _p(bn), _p(s1), _p(s2), _p(g_s1), _p(g_s2), _p(self.gd),
+              _p(self.sums) if bn is not None else None, st)
+        coef = None
+        if bn is not None:
+            _call("mmx_bn_coef", _p(self.sums), Cn, float(B * T * E), _p(self.bn), _p(self.coef), _p(bn_grads[0]), _p(bn_grads[1]), st)
+            if not self.trained:
+                self.coef[Cn:3 * Cn].zero_()
+            coef = self.coef
+        _call("mmx_conv_tail_bwd2", C_.byref(desc), _p(self.z), _p(dy), _p(self.gd), _p(bn), _p(coef), _p(self.dz), st)
+        _call("mmx_conv2d_large_wgrad", C_.byref(desc), _p(self.dz), _p(self.n), _p(g_cw), _p(g_cb), st)
+        _call("mmx_conv2d_large_fwd", C_.byref(desc), 1, _p(self.dz), _p(cw), None, _p(self.dn), st)
+        _call("mmx_ln_bwd", B * Cn * T, E, 0, _p(x), _p(self.stats), _p(ln_w), _p(self.dn), _p(dy), _p(dx), _p(g_ln_w), _p(g_ln_b), st)
+        return dx
+
+    @staticmethod
+    def launches(with_bn):
+        return (5 if with_bn else 3), (7 if with_bn else 6)
+
+
+class _ConvHalfLarge(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, meta, bnm, *tensors):
+        x = _chk(x, "x")
+        params = [None if q is None else _chk(q, "parameter") for q in tensors[:6]]
+        B, C, T, E = x.shape
+        desc = conv_half_desc(B, C, T, E, *meta)
+        needs_grad = any(ctx.needs_input_grad)
+        with torch.cuda.device_of(x):
+            run = ConvHalfLarge(B, C, T, E, x.device, need_backward=needs_grad, with_bn=bnm is not None)
+            y = torch.empty_like(x)
+            run.forward(desc, x, y, params, bnm)
+        ctx.run, ctx.params, ctx.x, ctx.meta, ctx.has_bn = run, params, x, meta, bnm is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _chk(dy, "grad")
+        run, params, x = ctx.run, ctx.params, ctx.x
+        B, C, T, E = x.shape
+        desc = conv_half_desc(B, C, T, E, *ctx.meta)
+        grads = _zeros_like_many(params)
+        bn_grads = None
+        if ctx.has_bn:
+            bn_grads = [torch.zeros(C, dtype=torch.float32, device=x.device), torch.zeros(C, dtype=torch.float32, device=x.device)]
+        dx = torch.empty_like(x)
+        with torch.cuda.device_of(x):
+            run.backward(desc, x, dy, dx, params, grads, bn_grads)
+        ctx.run = None
+        return (dx, None, None, *grads, *(bn_grads or []))
+
+
+def conv_half_large(x, meta, params, bn_module=None):
+    """One ConvMixerBlock half through the stage-kernel chain (large shapes; BatchNorm with max squeeze)."""
+    extra = [bn_module.weight, bn_module.bias] if bn_module is not None else []
+    return _ConvHalfLarge.apply(x, meta, bn_module, *params, *extra)
+
+
 class _SeTail(torch.autograd.Function):
     """mode_conv='once': y = x + se(x), or 2x without SE (conv_mixer_model.py:259-263,287-292)."""
 

@@ -193,12 +193,16 @@ class _ConvMixerPlan:
         # ops in execution order: ("half", block, half, params table, grads table) | ("tail", block, se ptrs)
         self.ops = []
         self.bn = {}                      # op index -> BatchNorm state of that half (regularization == -1)
+        self.large = {}                   # op index -> stage-kernel chain of a half the fused kernels do not serve
         for mb in model.Mixer_Block:
             for half in ((0, 1) if mb.mode_conv == "twice" else (0,)):
                 hp = mb.half_params(half)
-                if mb.regularization == -1.0:
-                    if mb.use_se and mb.use_max_pooling:
-                        raise NotImplementedError("TrainStep: BatchNorm with use_max_pooling=True is not built")
+                if mb.uses_large_path(half, B):
+                    reg = (mb.conv1 if half == 0 else mb.conv2).reg if mb.regularization == -1.0 else None
+                    self.large[len(self.ops)] = dict(
+                        run=F_.ConvHalfLarge(B, C, T, E, dev, with_bn=reg is not None), params=hp, grads=[flat.grad_of(q) for q in hp],
+                        reg=reg, bn_grads=None if reg is None else [flat.grad_of(reg.weight), flat.grad_of(reg.bias)])
+                elif mb.regularization == -1.0:
                     reg = (mb.conv1 if half == 0 else mb.conv2).reg
                     self.bn[len(self.ops)] = dict(
                         reg=reg, z=torch.empty(B, C, T, E, device=dev), gd=torch.empty(B, T, 2, device=dev),
@@ -216,8 +220,9 @@ class _ConvMixerPlan:
         self.head_w = F_.conv_head_table(hp)
         self.head_g = F_.conv_head_table([flat.grad_of(q) for q in hp])
         self.head_desc = L.MmxConvHeadDesc(B, C, T, To, E, Dout)
-        self.n_launches_fwd = 2 + len(self.ops)
-        self.n_launches_bwd = 1 + len(self.ops) + (2 if self.Hn == 0 else 3)
+        self.n_launches_fwd = 2 + len(self.ops) + sum(F_.ConvHalfLarge.launches(v["reg"] is not None)[0] - 1 for v in self.large.values())
+        self.n_launches_bwd = (1 + len(self.ops) + (2 if self.Hn == 0 else 3)
+                               + sum(F_.ConvHalfLarge.launches(v["reg"] is not None)[1] - 1 for v in self.large.values()))
 
     def _desc(self, mb, half, training):
         m = mb.half_meta(half, self.seed, 0)
@@ -234,7 +239,10 @@ class _ConvMixerPlan:
         L.check(lib, lib.mmx_pose_encoder_fwd(C.byref(self.enc_desc), C.byref(self.enc_w), _p(self.x), _p(self.m), _p(self.acts[0]), st),
                 "mmx_pose_encoder_fwd")
         for i, (kind, mb, half, tw, _) in enumerate(self.ops):
-            if kind == "half" and i in self.bn:
+            if kind == "half" and i in self.large:
+                lg = self.large[i]
+                lg["run"].forward(self._desc(mb, half, training), self.acts[i], self.acts[i + 1], lg["params"], lg["reg"])
+            elif kind == "half" and i in self.bn:
                 b = self.bn[i]
                 d = self._desc(mb, half, training)
                 if training:
@@ -262,7 +270,10 @@ class _ConvMixerPlan:
         for i in reversed(range(len(self.ops))):
             kind, mb, half, tw, tg = self.ops[i]
             nxt = self.dact[1] if cur is self.dact[0] else self.dact[0]
-            if kind == "half" and i in self.bn:
+            if kind == "half" and i in self.large:
+                lg = self.large[i]
+                lg["run"].backward(self._desc(mb, half, True), self.acts[i], cur, nxt, lg["params"], lg["grads"], lg["bn_grads"])
+            elif kind == "half" and i in self.bn:
                 b = self.bn[i]
                 d = self._desc(mb, half, True)
                 Bn, Cn, Tn, En = self.acts[i].shape
