@@ -1,8 +1,9 @@
 """Which ConvMixerBlock shapes do the fused half kernels serve?  Tabulates mmx_conv_half_plan (the planner behind
 mmx_conv_half_{fwd,bwd}: shared-memory budget 227 KB, weight-gradient tiling) over the reference's Optuna grid
 (optuna_search/conv_optuna_main.py:339-342: C = 8, E = 192, kT in {1,5,9}, kP in {1,5,...,29}; conv2 kernel rule
-conv_mixer_model.py:243) and the other configurations the reference uses.  Runs on the CPU build of the launch layer
-(tests/emu: same planner, same budget) when no GPU is present.
+conv_mixer_model.py:243) and the other configurations the reference uses.  "S=.. ..K": served by the fused kernels (sequences per
+CTA tile, dynamic shared memory); "chain": served by the stage-kernel chain (csrc/mmx_api_conv_large.cu, functional.ConvHalfLarge).
+Runs on the CPU build of the launch layer (tests/emu: same planner, same budget) when no GPU is present.
 
     python tools/conv_support_table.py [--markdown]
 """
@@ -32,7 +33,7 @@ def plan(lb, B, Cn, T, E, kt, kp, bwd):
     if rc == 0:
         return "S=%d %dK" % (S.value, smem.value // 1024)
     msg = lb.mmx_last_error().decode()
-    return "NO (%s)" % ("weight-gradient tiling" if "weight-gradient" in msg else "shared memory")
+    return "chain (%s)" % ("weight-gradient tiling" if "weight-gradient" in msg else "tile > shared memory")
 
 
 def main():
