@@ -188,7 +188,7 @@ def test_angle_l1_loss_kernel_and_rollout_with_the_angle_loss():
     loss2, predict2 = autoregressive_process_batch(batch, model, args, dim_used, True, loss_fn=torch_l1)
     loss2.backward()
     assert abs(float(loss) - float(loss2)) <= 1e-5 * abs(float(loss2))
-    assert torch.equal(predict, predict2)
+    assert (predict - predict2).abs().max().item() <= 2e-6 * predict2.abs().max().item()     # (the encoder's split-K partial sums combine in any order)
     scale = max(p.grad.abs().max().item() for p in model.parameters())
     for k, p in model.named_parameters():
         assert (p.grad - grads[k]).abs().max().item() <= 2e-5 * scale, k       # same dL/dpred; the kernels' atomics reorder sums

@@ -1,7 +1,7 @@
 """Large-batch throughput sweep (BASELINE.json configs[4]): batch 16K-256K sequences per GPU x hidden dim 64-512, MlpMixer and
 ConvMixer, one JSON line per cell (throughput, block-granular HBM roofline fraction, the kernels that served it, or the error
 an unsupported cell returns).  Single GPU: `python tools/sweep.py`; N GPUs: under torchrun (weak scaling, per-GPU batch fixed,
-one captured NCCL all-reduce per step).  env: SWEEP_H, SWEEP_B, SWEEP_E (comma lists), SWEEP_FAMILIES=mlp,conv, SWEEP_CPU=1
+gradient exchange fused into the Adam kernel over NVLink peer memory).  env: SWEEP_H, SWEEP_B, SWEEP_E (comma lists), SWEEP_FAMILIES=mlp,conv, SWEEP_CPU=1
 adds the reference's CPU step (oracle/_ref, 1024-sequence slice, all host threads) once per width.
 """
 import json
