@@ -24,7 +24,7 @@ extern "C" int mmx_peer_free(void*) { return fail(MMX_E_UNSUPPORTED, "mmx_peer_f
 extern "C" int mmx_ipc_export(void*, unsigned char*) { return fail(MMX_E_UNSUPPORTED, "mmx_ipc_export: not in the emulator"); }
 extern "C" int mmx_ipc_open(const unsigned char*, void**) { return fail(MMX_E_UNSUPPORTED, "mmx_ipc_open: not in the emulator"); }
 extern "C" int mmx_ipc_close(void*) { return fail(MMX_E_UNSUPPORTED, "mmx_ipc_close: not in the emulator"); }
-extern "C" int mmx_peer_flag_bytes(int world) { return 2 * world * 64 * 4; }
+extern "C" int mmx_peer_flag_bytes(int world) { return 2 * world * 128 * 4; }
 extern "C" int mmx_adam_step_peer(float*, float*, float*, const void*, const void*, int, int, long long, const float*, unsigned int*, void*) {
     return fail(MMX_E_UNSUPPORTED, "mmx_adam_step_peer: not in the emulator");
 }
@@ -36,7 +36,7 @@ int* mmx_tc5_abort_ptr();
 
 namespace {
 
-constexpr int kPeerCtas = 64;        // CTAs (= chunks of the bucket = flag slots per rank and phase)
+constexpr int kPeerCtas = 128;       // flag slots per rank and phase = upper bound of the grid (CTA c owns chunk c of the bucket)
 constexpr int kPeerThreads = 256;
 constexpr int kMaxWorld = 16;
 
@@ -49,6 +49,7 @@ struct PeerArgs {
     int* abort_count;
     long long n;
     int rank, world;
+    int grid;                            // CTAs of this launch (the same on every rank: a function of n only)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -69,7 +70,7 @@ __device__ __forceinline__ bool wait_flag(const unsigned int* flag, unsigned int
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) != want) {
         if (clock64() - t0 > 30000000000ll) { *timed_out = 1; return false; }
-        __nanosleep(64);
+        __nanosleep(32);
     }
     return true;
 }
@@ -77,16 +78,13 @@ __device__ __forceinline__ bool wait_flag(const unsigned int* flag, unsigned int
 __global__ void __launch_bounds__(kPeerThreads) adam_peer_kernel(const PeerArgs a) {
     __shared__ unsigned int s_epoch;
     __shared__ int s_timeout;
-    const int tid = threadIdx.x, c = blockIdx.x, W = a.world, G = kPeerCtas;
+    const int tid = threadIdx.x, c = blockIdx.x, W = a.world, G = kPeerCtas, NG = a.grid;
     if (tid == 0) { s_epoch = a.epoch[0] + 1u; s_timeout = 0; }
     __syncthreads();
     const unsigned int e = s_epoch;
     unsigned int* mine = a.peer_flags[a.rank];
     // ---- 1. arrive: this rank's gradients are final (they were written by earlier kernels of this stream)
-    if (tid < W) {
-        __threadfence_system();
-        st_release_sys(a.peer_flags[tid] + (0 * W + a.rank) * G + c, e);
-    }
+    if (tid < W) st_release_sys(a.peer_flags[tid] + (0 * W + a.rank) * G + c, e);
     // ---- 2. every peer has arrived
     if (tid < W) wait_flag(mine + (0 * W + tid) * G + c, e, &s_timeout);
     __syncthreads();
@@ -95,7 +93,7 @@ __global__ void __launch_bounds__(kPeerThreads) adam_peer_kernel(const PeerArgs 
     const float lr = a.hp[0], b2 = a.hp[2], eps = a.hp[3], wd = a.hp[4];
     const float bc1 = a.hp[5], bc2s = a.hp[6], gs = a.hp[7], omb1 = a.hp[8], omb2 = a.hp[9];
     const float step = lr / bc1;
-    const long long n4 = a.n >> 2, stride = (long long)G * kPeerThreads, i0 = (long long)c * kPeerThreads + tid;
+    const long long n4 = a.n >> 2, stride = (long long)NG * kPeerThreads, i0 = (long long)c * kPeerThreads + tid;
     const float* pg[kMaxWorld];
 #pragma unroll
     for (int r = 0; r < kMaxWorld; ++r) pg[r] = r < W ? a.peer_g[r] : nullptr;
@@ -131,10 +129,7 @@ __global__ void __launch_bounds__(kPeerThreads) adam_peer_kernel(const PeerArgs 
         if (i0 + k * stride < n4) held[k] = reduce4(i0 + k * stride);
     for (long long i = i0 + kHold * stride; i < n4; i += stride) adam4(i, reduce4(i));      // buckets above 1 M floats: the rest, fused
     __syncthreads();
-    if (tid < W) {
-        __threadfence_system();
-        st_release_sys(a.peer_flags[tid] + (1 * W + a.rank) * G + c, e);
-    }
+    if (tid < W) st_release_sys(a.peer_flags[tid] + (1 * W + a.rank) * G + c, e);      // (the CTA's peer loads completed before the barrier)
 #pragma unroll
     for (int k = 0; k < kHold; ++k)
         if (i0 + k * stride < n4) adam4(i0 + k * stride, held[k]);
@@ -144,7 +139,7 @@ __global__ void __launch_bounds__(kPeerThreads) adam_peer_kernel(const PeerArgs 
     if (tid == 0) {
         if (s_timeout) atomicAdd(a.abort_count, 1);
         __threadfence();
-        if (atomicAdd(a.epoch + 1, 1u) == (unsigned int)(G - 1)) {       // the last CTA publishes the epoch for the next launch
+        if (atomicAdd(a.epoch + 1, 1u) == (unsigned int)(NG - 1)) {       // the last CTA publishes the epoch for the next launch
             a.epoch[1] = 0u;
             __threadfence();
             a.epoch[0] = e;
@@ -204,7 +199,10 @@ extern "C" int mmx_adam_step_peer(float* p, float* m, float* v, const void* peer
     PeerArgs a;
     a.p = p; a.m = m; a.v = v; a.peer_g = (const float* const*)peer_g; a.peer_flags = (unsigned int* const*)peer_flags; a.hp = hyper;
     a.epoch = epoch; a.abort_count = mmx_tc5_abort_ptr(); a.n = n; a.rank = rank; a.world = world;
-    adam_peer_kernel<<<kPeerCtas, kPeerThreads, 0, (cudaStream_t)stream>>>(a);
+    // two float4 per thread: K2 (30 K floats) 16 CTAs, K4 (183 K) 90 CTAs; fewer CTAs = fewer flags crossing NVLink
+    long long want = ((n >> 2) + 2 * kPeerThreads - 1) / (2 * kPeerThreads);
+    a.grid = (int)(want < 16 ? 16 : (want > kPeerCtas ? kPeerCtas : want));
+    adam_peer_kernel<<<a.grid, kPeerThreads, 0, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(MMX_E_CUDA, "mmx_adam_step_peer: kernel launch: %s", cudaGetErrorString(e));
     return MMX_OK;
