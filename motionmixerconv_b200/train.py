@@ -552,7 +552,8 @@ class TrainStep:
         # data parallel: the NCCL all-reduce CAN be captured into the same graph (MMX_DP_GRAPH_ALLREDUCE=1), but measured on
         # 8 x B200 the captured collective has a heavy tail (median step 0.918 ms, mean 1.55 ms) while the eager call between
         # two graphs is steady (0.914 / 0.914 ms): two graphs + eager all-reduce is the default
-        one_graph = self.world == 1 or self.peer is not None or os.environ.get("MMX_DP_GRAPH_ALLREDUCE", "0") == "1"
+        one_graph = (self.world == 1 or (self.peer is not None and os.environ.get("MMX_DP_PEER_GRAPHS", "1") != "2")
+                     or os.environ.get("MMX_DP_GRAPH_ALLREDUCE", "0") == "1")
         self.graph_a = torch.cuda.CUDAGraph()
         if one_graph:
             # ONE graph per step: forward, backward, the NCCL all-reduce of the flat gradient bucket (NCCL collectives are
