@@ -5,7 +5,8 @@
 // device buffer owned by the library, ONE PER (device, weight matrix): keyed by the fc1 weight pointer, so two streams that
 // run the same block concurrently write identical bytes and different blocks never share a buffer.  Buffers are allocated on
 // first use (cudaMalloc: not legal while a stream capture is under way -- run the step once eagerly first, as TrainStep does)
-// and live until the process ends.
+// and live until the process ends (captured CUDA graphs hold their addresses, so they are never freed: 129 KB per distinct fc1
+// weight matrix the process ever runs).
 #include "mmx_launch.cuh"
 
 #if defined(MMX_HOST_EMU)
