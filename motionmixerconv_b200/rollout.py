@@ -129,11 +129,20 @@ class RolloutTrainer:
         loss, predict = tr.step(batch)          # static tensors, valid until the next step
     """
 
-    def __init__(self, model, args, dim_used, teacher_forcing=False, lr=1e-3, weight_decay=1e-5, use_cuda_graph=True):
+    def __init__(self, model, args, dim_used, teacher_forcing=False, lr=1e-3, weight_decay=1e-5, use_cuda_graph=True, process_group=None):
+        """``process_group``: batch-sharded data parallelism (every rank rolls out its own shard; the gradient exchange is part
+        of the fused optimiser step, see FusedAdam).  BatchNorm statistics stay per replica; model buffers are broadcast from
+        rank 0 at construction."""
         from .train import FusedAdam
         self.model, self.args, self.teacher_forcing = model, args, teacher_forcing
         self.dim_used = dim_used          # index tensor on the device is made at the first step (no host->device copy inside the capture)
-        self.opt = FusedAdam(model.parameters(), lr=lr, weight_decay=weight_decay)
+        self.opt = FusedAdam(model.parameters(), lr=lr, weight_decay=weight_decay, process_group=process_group)
+        if process_group is not None:
+            import torch.distributed as dist
+            for gi, group in enumerate(self.opt.param_groups):      # flat buffers + rank 0's parameters now (not inside the capture warm-up)
+                self.opt._flatten(gi, group)
+            for b in model.buffers():
+                dist.broadcast(b, src=dist.get_global_rank(process_group, 0), group=process_group)
         self.use_graph = use_cuda_graph
         self.graph = None
         self.batch = None

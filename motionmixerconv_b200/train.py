@@ -591,9 +591,14 @@ class FusedAdam(torch.optim.Optimizer):
     the first step; gradients produced by autograd are gathered into the flat gradient buffer.
     """
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None):
+        """``process_group``: batch-sharded data parallelism (one process per GPU): rank 0's parameters are broadcast at the
+        first step, every step SUMs the flat gradient bucket over the group and applies 1 / world -- by default inside the
+        Adam kernel over NVLink peer memory (mmx_adam_step_peer), else (MMX_DP_PEER=0, peers not mappable) an NCCL all-reduce."""
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._flat = {}
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if process_group is not None else 1
 
     def _flatten(self, gi, group):
         ps = [p for p in group["params"] if p.requires_grad]
@@ -614,7 +619,18 @@ class FusedAdam(torch.optim.Optimizer):
                   hyper=torch.tensor([group["lr"], group["betas"][0], group["betas"][1], group["eps"], group["weight_decay"], 1.0, 1.0, 1.0,
                                       1 - group["betas"][0], 1 - group["betas"][1]],
                                      dtype=torch.float32, device=dev),
-                  step=torch.zeros(1, dtype=torch.int32, device=dev), lr=group["lr"])
+                  step=torch.zeros(1, dtype=torch.int32, device=dev), lr=group["lr"], peer=None)
+        if self.world > 1:
+            st["hyper"][7:8].fill_(1.0 / self.world)
+            dist.broadcast(flat, src=dist.get_global_rank(self.pg, 0), group=self.pg)      # replicas start identical
+            if os.environ.get("MMX_DP_PEER", "1") != "0":
+                try:
+                    st["peer"] = P_.PeerGradBucket(o, dev, self.pg)
+                    st["g"] = st["peer"].g
+                except Exception as exc:                     # noqa: BLE001 -- any failure here means "use NCCL"
+                    st["peer"] = None
+                    if dist.get_rank(self.pg) == 0:
+                        print("FusedAdam: peer-memory gradient exchange unavailable (%s); using the NCCL all-reduce" % exc, file=sys.stderr)
         self._flat[gi] = st
         return st
 
@@ -639,6 +655,11 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.cuda.device(st["p"].device):
                 stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
                 L.check(lib, lib.mmx_adam_advance(_p(st["hyper"]), _p(st["step"]), stream), "mmx_adam_advance")
-                L.check(lib, lib.mmx_adam_step(_p(st["p"]), _p(st["g"]), _p(st["m"]), _p(st["v"]), st["p"].numel(),
-                                               _p(st["hyper"]), stream), "mmx_adam_step")
+                if st["peer"] is not None:                   # all-reduce over peer memory + Adam, one kernel (collective)
+                    st["peer"].adam_step(st["p"], st["m"], st["v"], st["hyper"], stream)
+                else:
+                    if self.world > 1:
+                        dist.all_reduce(st["g"], op=dist.ReduceOp.SUM, group=self.pg)
+                    L.check(lib, lib.mmx_adam_step(_p(st["p"]), _p(st["g"]), _p(st["m"]), _p(st["v"]), st["p"].numel(),
+                                                   _p(st["hyper"]), stream), "mmx_adam_step")
         return loss

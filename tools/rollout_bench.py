@@ -1,7 +1,9 @@
 """BASELINE.json configs[2]: ConvMixer AIS-shaped autoregressive rollout (25-frame prediction = 5 chained 10 -> 5 passes),
 training (BPTT through the predictions + Adam, RolloutTrainer graph) and inference (RolloutExecutor graph), at the
 reference's batch size 50 and at 256 / 4096, next to the eager path and the reference's CPU step (reference modules from
-oracle/_ref driven by the same loop on the host cores).  One JSON line per cell."""
+oracle/_ref driven by the same loop on the host cores).  One JSON line per cell.  Under torchrun (N GPUs): every rank rolls out its
+own batch of B sequences (weak scaling), the training step exchanges gradients inside the fused optimiser; values are whole-job
+(N x B / max-over-ranks time); the eager and CPU cells are skipped."""
 import json
 import os
 import sys
@@ -16,6 +18,14 @@ from motionmixerconv_b200.conv_mixer_model import ConvMixer
 from motionmixerconv_b200.rollout import RolloutExecutor, RolloutTrainer, autoregressive_process_batch
 from motionmixerconv_b200.train import FusedAdam
 from tests.synthetic import synthetic_full_windows
+
+RANK, WORLD, LOCAL = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(LOCAL)
+PG = None
+if WORLD > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
+    PG = dist.group.WORLD
 
 CFG = dict(num_blocks=6, dimPosIn=33, dimPosEmb=192, dimPosOut=33, in_nTP=10, out_nTP=5, conv_nChan=4, conv1_kernel_shape=(5, 9),
            mode_conv="twice", activation="mish", regularization=-1.0, use_se=True, r_se=8, encoder_n_harmonic_functions=0, encoder_omega0=0)
@@ -33,7 +43,12 @@ def timed(fn, n, warm=3):
         fn()
     e.record()
     torch.cuda.synchronize()
-    return s.elapsed_time(e) / n
+    ms = s.elapsed_time(e) / n
+    if WORLD > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return ms
 
 
 def cpu_cell(B, train):
@@ -72,13 +87,27 @@ def cpu_cell(B, train):
 
 for B in [int(v) for v in os.environ.get("ROLLOUT_B", "50,256,4096").split(",")]:
     torch.manual_seed(0)
-    batch = torch.from_numpy(synthetic_full_windows(B, 35, 33, scale="ais", seed=1)).cuda()
-    cell = {"workload": "ConvMixer AIS autoregressive rollout (K3: BatchNorm, C=4, E=192, k=(5,9), 6 blocks), 10 -> 25 frames as 5 chained passes", "B": B}
+    batch = torch.from_numpy(synthetic_full_windows(B, 35, 33, scale="ais", seed=1 + RANK)).cuda()
+    cell = {"workload": "ConvMixer AIS autoregressive rollout (K3: BatchNorm, C=4, E=192, k=(5,9), 6 blocks), 10 -> 25 frames as 5 chained passes",
+            "per_gpu_batch": B, "n_gpus": WORLD}
     # training, graph
     model = ConvMixer(**CFG).cuda().train()
-    tr = RolloutTrainer(model, ARGS, DIM, teacher_forcing=False)
+    tr = RolloutTrainer(model, ARGS, DIM, teacher_forcing=False, process_group=PG)
     ms = timed(lambda: tr.step(batch), 10)
-    cell["train_graph"] = {"ms": ms, "value": B / ms * 1e3, "unit": "sequences/s", "nan": bool(tr.nan_flag)}
+    cell["train_graph"] = {"ms": ms, "value": WORLD * B / ms * 1e3, "unit": "sequences/s", "nan": bool(tr.nan_flag)}
+    if WORLD > 1:
+        pmax, pmin = tr.opt._flat[0]["p"].clone(), tr.opt._flat[0]["p"].clone()
+        dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
+        cell["dp_params_identical"] = bool(torch.equal(pmax, pmin))
+        ex = RolloutExecutor(model.eval(), 10, 25, 10, 5, 5)
+        ms = timed(lambda: ex(batch), 20)
+        cell["infer_graph"] = {"ms": ms, "value": WORLD * B / ms * 1e3, "unit": "sequences/s"}
+        if RANK == 0:
+            print(json.dumps(cell), flush=True)
+        del model, tr, ex
+        torch.cuda.empty_cache()
+        continue
     # training, eager autograd (what round 1 had)
     model2 = ConvMixer(**CFG).cuda().train()
     opt = FusedAdam(model2.parameters(), lr=1e-3, weight_decay=1e-5)
@@ -100,3 +129,9 @@ for B in [int(v) for v in os.environ.get("ROLLOUT_B", "50,256,4096").split(",")]
     print(json.dumps(cell), flush=True)
     del model, model2, tr, ex, opt
     torch.cuda.empty_cache()
+
+if WORLD > 1:
+    import threading
+    threading.Timer(15.0, lambda: os._exit(0)).start()
+    dist.destroy_process_group()
+    os._exit(0)
