@@ -153,3 +153,28 @@ def test_emulated_conv_dropout_masks_consistent_between_forward_and_backward():
         fd = (np.sum(fwd(x, pp).astype(np.float64) * r) - np.sum(fwd(x, pm).astype(np.float64) * r)) / (2 * eps)
         an = float(np.sum(grads[idx].astype(np.float64) * dv))
         assert abs(fd - an) <= 3e-2 * max(abs(an), 1.0), (idx, fd, an)
+
+
+def test_conv_half_plan_capability_query():
+    """mmx_conv_half_plan on the CPU build of the launch layer (same planner, same 227 KB budget as the B200 build): the
+    reference's default shapes are served by the fused kernels, the wide Optuna-grid shapes are not (the module then routes
+    them to the stage-kernel chain, functional.ConvHalfLarge)."""
+    import ctypes as C
+    from motionmixerconv_b200 import _lib as L
+    from tests.emu.harness import emu
+    lib = emu()
+
+    def plan(Cn, E, kt, kp, bwd):
+        d = L.MmxConvHalfDesc(256, Cn, 10, E, kt, kp, (kt - 1) // 2, (kp - 1) // 2, 1, 1, 1, 0, 1, 0, L.MmxDropout(0.0, 0, 0, None))
+        S, smem = C.c_int(0), C.c_int(0)
+        rc = lib.mmx_conv_half_plan(C.byref(d), int(bwd), C.byref(S), C.byref(smem))
+        return rc, S.value, smem.value
+
+    for bwd in (0, 1):
+        rc, S, smem = plan(1, 50, 1, 3, bwd)            # train_mixer_h36m.py __main__ config
+        assert rc == 0 and S >= 4 and 0 < smem <= 227 * 1024
+        rc, S, smem = plan(4, 192, 5, 9, bwd)           # the AIS autoregressive config (K3)
+        assert rc == 0 and S == 1
+        rc, _, _ = plan(8, 192, 9, 29, bwd)             # Optuna grid, optuna_search/conv_optuna_main.py:339-342
+        assert rc == -2 and b"shared memory" in lib.mmx_last_error() or b"weight-gradient" in lib.mmx_last_error()
+    assert plan(9, 50, 1, 3, 0)[0] == -2                # conv_nChan > 8
