@@ -68,16 +68,28 @@ class PeerGradBucket:
         g_bytes = (self.numel * 4 + 255) // 256 * 256
         flag_bytes = int(lib.mmx_peer_flag_bytes(self.world))
         with torch.cuda.device(device):
-            ptr = C.c_void_p()
-            L.check(lib, lib.mmx_peer_alloc(g_bytes + flag_bytes, C.byref(ptr)), "mmx_peer_alloc")
-            self.ptr = ptr.value
-            handle = C.create_string_buffer(64)
-            L.check(lib, lib.mmx_ipc_export(self.ptr, handle), "mmx_ipc_export")
-            handles = [None] * self.world
-            dist.all_gather_object(handles, (bytes(handle.raw), torch.cuda.current_device()), group=group)
             me = torch.cuda.current_device()
-            peers, self._opened, err = [], [], None
-            for r, (h, peer_dev) in enumerate(handles):
+            # every step of the set-up is collective: a rank that fails locally still takes part in the exchanges, and all ranks
+            # take the same decision at the end (a rank raising alone would leave its peers blocked in a collective)
+            err, handle_bytes, self.ptr = None, b"", None
+            ptr = C.c_void_p()
+            if lib.mmx_peer_alloc(g_bytes + flag_bytes, C.byref(ptr)) != 0:
+                err = "mmx_peer_alloc: %s" % (lib.mmx_last_error() or b"?").decode()
+            else:
+                self.ptr = ptr.value
+                handle = C.create_string_buffer(64)
+                if lib.mmx_ipc_export(self.ptr, handle) != 0:
+                    err = "mmx_ipc_export: %s" % (lib.mmx_last_error() or b"?").decode()
+                else:
+                    handle_bytes = bytes(handle.raw)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (handle_bytes, me, err), group=group)
+            peers, self._opened = [], []
+            if err is None and any(h[2] for h in handles):
+                err = "a peer could not allocate / export its bucket"
+            for r, (h, peer_dev, _) in enumerate(handles):
+                if err:
+                    break
                 if r == self.rank:
                     peers.append(self.ptr)
                     continue
@@ -85,17 +97,18 @@ class PeerGradBucket:
                     err = "rank %d shares device %d with this rank" % (r, me)
                     break
                 q = C.c_void_p()
-                rc = lib.mmx_ipc_open(h, C.byref(q))
-                if rc != 0:
+                if lib.mmx_ipc_open(h, C.byref(q)) != 0:
                     err = "rank %d: %s" % (r, (lib.mmx_last_error() or b"?").decode())
                     break
                 peers.append(q.value)
                 self._opened.append(q.value)
-            # every rank must take the same decision
             ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=device)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
             if int(ok.item()) == 0:
                 self.close()
+                if self.ptr is not None:
+                    lib.mmx_peer_free(self.ptr)
+                    self.ptr = None
                 raise RuntimeError("PeerGradBucket: peer mapping unavailable (%s)" % (err or "on another rank"))
             self.peer_g = torch.tensor(peers, dtype=torch.int64, device=device)
             self.peer_flags = torch.tensor([q + g_bytes for q in peers], dtype=torch.int64, device=device)
