@@ -65,9 +65,14 @@ int plan_head(const MmxMlpHeadDesc* d, bool bwd, MlpHeadDims* out, size_t* smem,
     MlpHeadDims h; h.B = d->B; h.T = d->T; h.To = d->To; h.H = d->H; h.D = d->D;
     const int two_cta_budget = (di.max_smem + 1024) / 2 - 2048;
     const int forced = env_int(bwd ? "MMX_HEAD_S_BWD" : "MMX_HEAD_S_FWD", 0);
-    for (int pass = 0; pass < 2; ++pass) {
+    // wide rows: one CTA per SM with a larger tile beats two CTAs with S = 2 (the forced-S sweep below ran in the full budget)
+    for (int pass = (d->H >= 64 && forced <= 0) ? 1 : 0; pass < 2; ++pass) {
         const int budget = pass == 0 ? two_cta_budget : di.max_smem;
-        for (int S = forced > 0 ? forced : imax(1, 96 / imax(d->T, d->To)); S >= 1; --S) {
+        // sequences per tile: ~96 output rows per tile for narrow models; wide rows (H >= 64: K4, H = 128) amortise the fc_out weight
+        // reads over more rows -- measured at B = 4096, T = 10, To = 25, H = 128, D = 54 (us, fwd / bwd): S = 2: 122 / 400, 4: 98 / 302,
+        // 6: 120 / 285 (tools/head_sweep.py)
+        const int rows0 = d->H >= 64 ? (bwd ? 160 : 100) : 96;
+        for (int S = forced > 0 ? forced : imax(1, rows0 / imax(d->T, d->To)); S >= 1; --S) {
             h.S = S;
             const size_t bytes = (size_t)mlp_head_smem(h, bwd).total * 4;
             if (bytes <= (size_t)budget) {
