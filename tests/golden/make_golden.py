@@ -48,6 +48,11 @@ CASES = {
     "mlp_bn": dict(family="mlp", B=8, scale="amass", cfg=dict(
         num_classes=33, num_blocks=2, hidden_dim=32, tokens_mlp_dim=20, channels_mlp_dim=32, seq_len=10,
         pred_len=10, activation="gelu", regularization=-1.0, input_size=33, r_se=8, use_se=True)),
+    # BatchNorm1d + the max squeeze, mish (mlp_mixer.py:21 with :72-73)
+    "mlp_bn_maxpool": dict(family="mlp", B=7, scale="amass", cfg=dict(
+        num_classes=33, num_blocks=2, hidden_dim=40, tokens_mlp_dim=12, channels_mlp_dim=24, seq_len=10,
+        pred_len=10, activation="mish", regularization=-1.0, input_size=33, r_se=4, use_max_pooling=True,
+        use_se=True)),
     # ---- ConvMixer ------------------------------------------------------------------
     "conv_k1": dict(family="conv", B=6, scale="h36m", cfg=dict(
         num_blocks=4, dimPosIn=66, dimPosEmb=50, dimPosOut=66, in_nTP=10, out_nTP=25, conv_nChan=1,
@@ -74,6 +79,16 @@ CASES = {
         num_blocks=2, dimPosIn=12, dimPosEmb=20, dimPosOut=12, in_nTP=6, out_nTP=4, conv_nChan=2,
         conv1_kernel_shape=(3, 3), mode_conv="once", activation="gelu", regularization=0, use_se=False,
         encoder_n_harmonic_functions=0, encoder_omega0=0)),
+    # the reference's Optuna grid (optuna_search/conv_optuna_main.py:339-342): C = 8, E = 192, a kernel beyond the fused kernels' tile
+    "conv_c8_k5x9": dict(family="conv", B=2, scale="ais", cfg=dict(
+        num_blocks=1, dimPosIn=33, dimPosEmb=192, dimPosOut=33, in_nTP=10, out_nTP=10, conv_nChan=8,
+        conv1_kernel_shape=(5, 9), mode_conv="twice", activation="mish", regularization=0, use_se=True,
+        r_se=8, encoder_n_harmonic_functions=0, encoder_omega0=0)),
+    # BatchNorm2d + the max squeeze (conv_mixer_model.py:60-62 with :115-116)
+    "conv_maxpool_bn": dict(family="conv", B=5, scale="ais", cfg=dict(
+        num_blocks=2, dimPosIn=33, dimPosEmb=64, dimPosOut=33, in_nTP=10, out_nTP=10, conv_nChan=4,
+        conv1_kernel_shape=(5, 5), mode_conv="twice", activation="gelu", regularization=-1.0, use_se=True,
+        r_se=4, use_max_pooling=True, encoder_n_harmonic_functions=0, encoder_omega0=0)),
     "conv_evenk": dict(family="conv", B=3, scale="ais", cfg=dict(
         num_blocks=1, dimPosIn=33, dimPosEmb=40, dimPosOut=33, in_nTP=10, out_nTP=10, conv_nChan=3,
         conv1_kernel_shape=(1, 29), mode_conv="twice", activation="gelu", regularization=0, use_se=True,

@@ -15,7 +15,9 @@ TOL = 1e-5
 # mathematically ZERO gradients (a per-channel constant in front of LayerNorms only): what any implementation returns is the
 # rounding noise of a long cancelling sum, which scales with the summands, not with the other gradients
 ZERO_GRAD_SLACK = {"encoder.channelUpscaling.bias": 50}
-CONV_CASES = golden_cases("conv")     # includes conv_k3_bn: BatchNorm2d halves (two-pass kernels)
+# includes conv_k3_bn: BatchNorm2d halves (two-pass kernels); the fixtures served by the stage-kernel chain (not in the emulator: plain
+# CUDA kernels) are excluded -- a tile beyond the fused kernels, BatchNorm with the max squeeze
+CONV_CASES = [c for c in golden_cases("conv") if c not in ("conv_c8_k5x9", "conv_maxpool_bn")]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)

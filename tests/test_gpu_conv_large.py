@@ -154,3 +154,34 @@ def test_trainstep_on_a_large_batchnorm_config(use_graph):
     losses = [float(ts.step(xs, gts)) for _ in range(3)]
     want = O.train_steps(O.ConvMixerOracle(cfg, params), x, gt, 3)
     np.testing.assert_allclose(losses, want, rtol=5e-5)
+
+
+def test_batchnorm_with_max_squeeze_golden():
+    """BatchNorm2d + use_max_pooling (conv_mixer_model.py:60-62 with :115-116) against the fixture generated from the reference:
+    training forward / backward, running statistics after one update, eval forward."""
+    g = Golden("conv_maxpool_bn")
+    model, _ = _build(g.cfg, g.params)
+    model.train()
+    assert all(mb.uses_large_path(0, len(g.x)) for mb in model.Mixer_Block)
+    pred, loss, grads, dx = _run(model, g.x, g.gt)
+    o64 = O.ConvMixerOracle(g.cfg, g.params, dtype=np.float64)
+    p64 = o64.forward(g.x)
+    _, dp64 = O.mpjpe(p64, g.gt.astype(np.float64))
+    g64, dx64 = o64.backward(dp64)
+    check_close("pred", pred, g.pred, p64, rtol=TOL)
+    assert abs(loss - g.loss) <= TOL * abs(g.loss)
+    floor = 5e-6 * grad_scale(g.grads)
+    for k, want in g.grads.items():
+        if ".se2." in k:
+            continue
+        check_close("grad " + k, grads[k], want, g64[k], rtol=TOL, atol=floor * (50 if k == "encoder.channelUpscaling.bias" else 1))
+    check_close("dx", dx, g.dx, dx64, rtol=TOL, atol=1e-6 * float(np.abs(g.dx).max()))
+    sd = model.state_dict()
+    for k in sd:
+        if "running_" in k:
+            np.testing.assert_allclose(sd[k].cpu().numpy(), g.params1[k], rtol=1e-5, atol=1e-7, err_msg=k)
+    fresh, _ = _build(g.cfg, g.params)
+    fresh.eval()
+    with torch.no_grad():
+        pe = fresh(torch.from_numpy(g.x).cuda()).cpu().numpy()
+    check_close("pred_eval", pe, g.pred_eval, rtol=TOL)

@@ -33,7 +33,7 @@ def _run(model, x, gt):
     return pred.detach().cpu().numpy(), float(loss.detach()), grads, xg.grad.cpu().numpy()
 
 
-MLP_CASES = [c for c in golden_cases("mlp") if c != "mlp_bn"]
+MLP_CASES = [c for c in golden_cases("mlp") if not c.startswith("mlp_bn")]
 
 
 @pytest.mark.parametrize("case", MLP_CASES)
@@ -144,8 +144,9 @@ def test_large_batch_size_independent_properties():
 
 
 # ---- BatchNorm1d inside the MLP blocks (regularization == -1; mlp_mixer.py:72-73, sampled by optuna_search/optuna_main.py:189-190)
-def test_batchnorm_golden_train_and_eval():
-    g = Golden("mlp_bn")
+@pytest.mark.parametrize("case", ["mlp_bn", "mlp_bn_maxpool"])
+def test_batchnorm_golden_train_and_eval(case):
+    g = Golden(case)
     model = _model(g.cfg, g.params).train()
     pred, loss, grads, dx = _run(model, g.x, g.gt)
     o64 = O.MlpMixerOracle(g.cfg, g.params, dtype=np.float64)
